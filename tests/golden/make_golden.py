@@ -1,0 +1,105 @@
+"""Generates tests/golden/*.npz from the REAL reference modules that import without
+TensorFlow in this container:
+
+  /root/reference/efficientdet/nms_np.py          (numpy only)
+  /root/reference/efficientdet/hparams_config.py  (with an empty `tensorflow` stub)
+  /root/reference/efficientdet/tf2/fpn_configs.py (same stub)
+
+Run from the repo root:  python tests/golden/make_golden.py
+The GPU box has no /root/reference; tests there read the committed .npz / .json files.
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = '/root/reference/efficientdet'
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+  if 'tensorflow' not in sys.modules:
+    sys.modules['tensorflow'] = types.ModuleType('tensorflow')  # only touched by yaml IO
+  sys.path.insert(0, REF)
+  import nms_np  # pylint: disable=g-import-not-at-top
+  import hparams_config  # pylint: disable=g-import-not-at-top
+  from tf2 import fpn_configs  # pylint: disable=g-import-not-at-top
+  return nms_np, hparams_config, fpn_configs
+
+
+def make_dets(rng, k, image=512.0, clusters=None):
+  """COCO-shaped boxes [x1,y1,x2,y2,score] float32 with distinct scores."""
+  if clusters:
+    centres = rng.uniform(0, image, size=(clusters, 2))
+    c = centres[rng.integers(0, clusters, size=k)] + rng.normal(0, 6.0, size=(k, 2))
+  else:
+    c = rng.uniform(0, image, size=(k, 2))
+  wh = np.exp(rng.uniform(np.log(8), np.log(image / 2), size=(k, 2)))
+  x1y1 = c - wh / 2
+  x2y2 = c + wh / 2
+  scores = 1.0 / (1.0 + np.exp(-rng.normal(-2.0, 2.0, size=k)))
+  # make scores distinct in float32 (argsort tie order is implementation-defined)
+  scores = np.unique(scores.astype(np.float32))
+  while scores.size < k:
+    extra = (1.0 / (1.0 + np.exp(-rng.normal(-2.0, 2.0, size=k)))).astype(np.float32)
+    scores = np.unique(np.concatenate([scores, extra]))
+  scores = rng.permutation(scores)[:k]
+  return np.column_stack([x1y1, x2y2, scores]).astype(np.float32)
+
+
+def main():
+  nms_np, hparams_config, fpn_configs = import_reference()
+  rng = np.random.default_rng(20260922)
+
+  # ---- nms_np goldens ---------------------------------------------------------------
+  cases = {}
+  methods = [
+      dict(method='hard', iou_thresh=None, score_thresh=0.0, sigma=None),
+      dict(method='hard', iou_thresh=0.3, score_thresh=0.0, sigma=None),
+      dict(method='diou', iou_thresh=None, score_thresh=0.0, sigma=None),
+      dict(method='gaussian', iou_thresh=None, score_thresh=0.0, sigma=None),
+      dict(method='gaussian', iou_thresh=None, score_thresh=0.05, sigma=0.3),
+      dict(method='linear', iou_thresh=None, score_thresh=0.0, sigma=None),
+  ]
+  for ci, (k, clusters) in enumerate([(1, None), (7, None), (100, 5), (1000, 40), (5000, 100)]):
+    dets = make_dets(rng, k, clusters=clusters)
+    for mi, cfg in enumerate(methods):
+      out = nms_np.nms(dets.copy(), dict(cfg))
+      cases['dets_%d' % ci] = dets
+      cases['out_%d_%d' % (ci, mi)] = np.asarray(out, np.float32)
+  cases['methods'] = np.asarray([json.dumps(m) for m in methods])
+  np.savez_compressed(os.path.join(OUT, 'nms_np_nms.npz'), **cases)
+
+  # per_class_nms goldens
+  pc = {}
+  for ci, k in enumerate([50, 600, 5000]):
+    d = make_dets(rng, k, clusters=max(2, k // 40))
+    boxes = d[:, [1, 0, 3, 2]].copy()  # [ymin,xmin,ymax,xmax] as produced by pre_nms
+    scores = d[:, 4].copy()
+    classes = rng.integers(0, 90, size=k).astype(np.int32)
+    for mi, cfg in enumerate(methods[:1] + methods[3:4]):
+      cfg = dict(cfg, max_output_size=100, pyfunc=True, max_nms_inputs=0)
+      out = nms_np.per_class_nms(boxes, scores, classes, np.asarray([ci], np.float32),
+                                 np.asarray([1.5], np.float32), 90, 100, cfg)
+      pc['out_%d_%d' % (ci, mi)] = out
+    pc['boxes_%d' % ci], pc['scores_%d' % ci], pc['classes_%d' % ci] = boxes, scores, classes
+  np.savez_compressed(os.path.join(OUT, 'nms_np_per_class.npz'), **pc)
+
+  # ---- registry / fpn goldens ---------------------------------------------------------
+  reg = {}
+  names = (list(hparams_config.efficientdet_model_param_dict) +
+           list(hparams_config.efficientdet_lite_param_dict))
+  for n in names:
+    reg[n] = hparams_config.get_efficientdet_config(n).as_dict()
+  fpn = {}
+  for lo, hi in [(3, 7), (2, 7), (3, 8)]:
+    fpn['%d-%d' % (lo, hi)] = fpn_configs.bifpn_config(lo, hi, None).as_dict()
+  with open(os.path.join(OUT, 'registry.json'), 'w') as f:
+    json.dump({'configs': reg, 'bifpn': fpn}, f, indent=1, sort_keys=True)
+  print('wrote goldens to', OUT)
+
+
+if __name__ == '__main__':
+  main()
