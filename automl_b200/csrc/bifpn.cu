@@ -1,0 +1,229 @@
+// BiFPN node kernel: resample each input to the node resolution (identity / TF1 nearest
+// upsample / 'SAME' max-pool), fast-normalised weighted fusion, activation, depthwise 3x3 'SAME'
+// -- one pass, the fused map only ever lives in shared memory.  Plus the stand-alone max-pool
+// used to create the extra P6.. levels.
+//
+// Memory-bound: bytes = 2*n*c*(sum_inputs h_i*w_i + h*w) + 2*9*c.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace edet {
+
+constexpr int kFuseThreads = 256;
+constexpr int kFuseTH = 8, kFuseTW = 16;   // output tile
+constexpr int kFuseCB = 32;                // channels per CTA
+constexpr int kFuseMaxIn = 3;
+
+struct FuseIn {
+  const __half* ptr;
+  int h, w, mode;
+  int pool_h, pool_w, stride_h, stride_w, pad_t, pad_l;
+  float scale_h, scale_w;  // in/out, float32 as TF computes it
+  float weight;
+};
+struct FuseParams {
+  FuseIn in[kFuseMaxIn];
+  int n_inputs;
+};
+
+__device__ __forceinline__ void load8(const __half* base, int hh, int ww, int c, int y, int x,
+                                      int ch, float* f) {
+  half8_to_float(__ldg(reinterpret_cast<const uint4*>(
+                     base + (static_cast<size_t>(y) * ww + x) * c + ch)), f);
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kFuseThreads)
+fuse_dw_kernel(const FuseParams p, const __half* __restrict__ dw_w, __half* __restrict__ out,
+               int h, int wd, int c, int chunks) {
+  constexpr int HT = kFuseTH + 2, WT = kFuseTW + 2, G = kFuseCB / 8;
+  __shared__ __align__(16) float fused[HT * WT][kFuseCB];
+  const int n = blockIdx.z / chunks;
+  const int c0 = (blockIdx.z % chunks) * kFuseCB;
+  const int y0 = blockIdx.y * kFuseTH, x0 = blockIdx.x * kFuseTW;
+  const int groups = min(G, (c - c0) >> 3);
+
+  // ---- phase 1: fused + activated map for the tile and its 1-pixel halo -------------------
+  for (int item = threadIdx.x; item < HT * WT * G; item += kFuseThreads) {
+    const int g = item % G, pix = item / G;
+    const int ty = pix / WT, tx = pix % WT;
+    const int y = y0 + ty - 1, x = x0 + tx - 1;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    if (g < groups && y >= 0 && y < h && x >= 0 && x < wd) {
+      const int ch = c0 + g * 8;
+      for (int i = 0; i < p.n_inputs; ++i) {
+        const FuseIn& fi = p.in[i];
+        const __half* base = fi.ptr + static_cast<size_t>(n) * fi.h * fi.w * c;
+        float v[8];
+        if (fi.mode == EDET_RS_SAME) {
+          load8(base, fi.h, fi.w, c, y, x, ch, v);
+        } else if (fi.mode == EDET_RS_UP) {
+          const int sy = min(static_cast<int>(floorf(__fmul_rn(static_cast<float>(y), fi.scale_h))), fi.h - 1);
+          const int sx = min(static_cast<int>(floorf(__fmul_rn(static_cast<float>(x), fi.scale_w))), fi.w - 1);
+          load8(base, fi.h, fi.w, c, sy, sx, ch, v);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = -CUDART_INF_F;
+          const int sy0 = y * fi.stride_h - fi.pad_t, sx0 = x * fi.stride_w - fi.pad_l;
+          for (int py = 0; py < fi.pool_h; ++py) {
+            const int sy = sy0 + py;
+            if (sy < 0 || sy >= fi.h) continue;
+            for (int px = 0; px < fi.pool_w; ++px) {
+              const int sx = sx0 + px;
+              if (sx < 0 || sx >= fi.w) continue;
+              float t[8];
+              load8(base, fi.h, fi.w, c, sy, sx, ch, t);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], t[e]);
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], fi.weight, acc[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = apply_act_t<ACT>(acc[e]);
+    }
+    float4* dst = reinterpret_cast<float4*>(&fused[pix][g * 8]);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  __syncthreads();
+
+  // ---- phase 2: depthwise 3x3 over the shared fused map -----------------------------------
+  for (int item = threadIdx.x; item < kFuseTH * kFuseTW * G; item += kFuseThreads) {
+    const int g = item % G, pix = item / G;
+    const int ty = pix / kFuseTW, tx = pix % kFuseTW;
+    const int y = y0 + ty, x = x0 + tx;
+    if (g >= groups || y >= h || x >= wd) continue;
+    const int ch = c0 + g * 8;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float wf[8];
+        half8_to_float(__ldg(reinterpret_cast<const uint4*>(dw_w + static_cast<size_t>(ky * 3 + kx) * c + ch)), wf);
+        const float4* src = reinterpret_cast<const float4*>(&fused[(ty + ky) * WT + tx + kx][g * 8]);
+        const float4 a = src[0], b = src[1];
+        acc[0] = fmaf(a.x, wf[0], acc[0]); acc[1] = fmaf(a.y, wf[1], acc[1]);
+        acc[2] = fmaf(a.z, wf[2], acc[2]); acc[3] = fmaf(a.w, wf[3], acc[3]);
+        acc[4] = fmaf(b.x, wf[4], acc[4]); acc[5] = fmaf(b.y, wf[5], acc[5]);
+        acc[6] = fmaf(b.z, wf[6], acc[6]); acc[7] = fmaf(b.w, wf[7], acc[7]);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * h + y) * wd + x) * c + ch) =
+        float_to_half8(acc);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+max_pool_kernel(const __half* __restrict__ in, __half* __restrict__ out, int h, int wd, int c,
+                int ho, int wo, int pool_h, int pool_w, int stride_h, int stride_w, int pad_t,
+                int pad_l, long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = c >> 3;
+  const int g = static_cast<int>(idx % cg);
+  long long r = idx / cg;
+  const int ox = static_cast<int>(r % wo);
+  r /= wo;
+  const int oy = static_cast<int>(r % ho);
+  const int n = static_cast<int>(r / ho);
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = -CUDART_INF_F;
+  const __half* base = in + static_cast<size_t>(n) * h * wd * c;
+  for (int py = 0; py < pool_h; ++py) {
+    const int sy = oy * stride_h - pad_t + py;
+    if (sy < 0 || sy >= h) continue;
+    for (int px = 0; px < pool_w; ++px) {
+      const int sx = ox * stride_w - pad_l + px;
+      if (sx < 0 || sx >= wd) continue;
+      float t[8];
+      load8(base, h, wd, c, sy, sx, g * 8, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], t[e]);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * ho + oy) * wo + ox) * c + g * 8) =
+      float_to_half8(v);
+}
+
+}  // namespace edet
+
+extern "C" int edet_fuse_dw(const edet_fuse_input* h_inputs, int n_inputs, const edet_half* dw_w,
+                            edet_half* out, int n, int h, int wd, int c, int act,
+                            edet_stream_t stream) {
+  using namespace edet;
+  EDET_CHECK_ARG(h_inputs && dw_w && out, "fuse_dw: null pointer");
+  EDET_CHECK_ARG(n_inputs >= 1 && n_inputs <= kFuseMaxIn, "fuse_dw: 1..3 inputs (got %d)", n_inputs);
+  EDET_CHECK_ARG(n > 0 && h > 0 && wd > 0 && c > 0 && c % 8 == 0, "fuse_dw: bad shape");
+  FuseParams p;
+  p.n_inputs = n_inputs;
+  for (int i = 0; i < n_inputs; ++i) {
+    const edet_fuse_input& s = h_inputs[i];
+    FuseIn& d = p.in[i];
+    EDET_CHECK_ARG(s.ptr != nullptr, "fuse_dw: input %d is null", i);
+    d.ptr = reinterpret_cast<const __half*>(s.ptr);
+    d.h = s.h; d.w = s.w; d.mode = s.mode; d.weight = s.weight;
+    d.pool_h = d.pool_w = d.stride_h = d.stride_w = 1; d.pad_t = d.pad_l = 0;
+    d.scale_h = d.scale_w = 1.f;
+    if (s.mode == EDET_RS_SAME) {
+      EDET_CHECK_ARG(s.h == h && s.w == wd, "fuse_dw: input %d is %dx%d, node is %dx%d", i, s.h, s.w, h, wd);
+    } else if (s.mode == EDET_RS_UP) {
+      EDET_CHECK_ARG(s.h <= h && s.w <= wd, "fuse_dw: input %d cannot be upsampled", i);
+      d.scale_h = static_cast<float>(s.h) / static_cast<float>(h);
+      d.scale_w = static_cast<float>(s.w) / static_cast<float>(wd);
+    } else if (s.mode == EDET_RS_DOWN) {
+      EDET_CHECK_ARG(ceil_div(s.h, s.stride_h) == h && ceil_div(s.w, s.stride_w) == wd,
+                     "fuse_dw: input %d pooled size mismatch", i);
+      d.pool_h = s.pool_h; d.pool_w = s.pool_w; d.stride_h = s.stride_h; d.stride_w = s.stride_w;
+      d.pad_t = same_pad_before(s.h, s.pool_h, s.stride_h);
+      d.pad_l = same_pad_before(s.w, s.pool_w, s.stride_w);
+    } else {
+      set_error("fuse_dw: bad mode %d", s.mode);
+      return EDET_ERR_INVALID;
+    }
+  }
+  const int chunks = ceil_div(c, kFuseCB);
+  dim3 grid(ceil_div(wd, kFuseTW), ceil_div(h, kFuseTH), n * chunks);
+  const __half* hw = reinterpret_cast<const __half*>(dw_w);
+  __half* ho = reinterpret_cast<__half*>(out);
+  cudaStream_t s = as_stream(stream);
+  switch (act) {
+    case EDET_ACT_SWISH: fuse_dw_kernel<EDET_ACT_SWISH><<<grid, kFuseThreads, 0, s>>>(p, hw, ho, h, wd, c, chunks); break;
+    case EDET_ACT_RELU6: fuse_dw_kernel<EDET_ACT_RELU6><<<grid, kFuseThreads, 0, s>>>(p, hw, ho, h, wd, c, chunks); break;
+    case EDET_ACT_RELU: fuse_dw_kernel<EDET_ACT_RELU><<<grid, kFuseThreads, 0, s>>>(p, hw, ho, h, wd, c, chunks); break;
+    case EDET_ACT_HSWISH: fuse_dw_kernel<EDET_ACT_HSWISH><<<grid, kFuseThreads, 0, s>>>(p, hw, ho, h, wd, c, chunks); break;
+    case EDET_ACT_NONE: fuse_dw_kernel<EDET_ACT_NONE><<<grid, kFuseThreads, 0, s>>>(p, hw, ho, h, wd, c, chunks); break;
+    default:
+      set_error("fuse_dw: bad activation %d", act);
+      return EDET_ERR_INVALID;
+  }
+  EDET_CHECK_LAUNCH();
+  return EDET_OK;
+}
+
+extern "C" int edet_max_pool(const edet_half* in, edet_half* out, int n, int h, int wd, int c,
+                             int pool_h, int pool_w, int stride_h, int stride_w,
+                             edet_stream_t stream) {
+  using namespace edet;
+  EDET_CHECK_ARG(in && out, "max_pool: null pointer");
+  EDET_CHECK_ARG(n > 0 && h > 0 && wd > 0 && c > 0 && c % 8 == 0, "max_pool: bad shape");
+  EDET_CHECK_ARG(pool_h > 0 && pool_w > 0 && stride_h > 0 && stride_w > 0, "max_pool: bad window");
+  const int ho = ceil_div(h, stride_h), wo = ceil_div(wd, stride_w);
+  const long long total = static_cast<long long>(n) * ho * wo * (c >> 3);
+  const int blocks = static_cast<int>((total + 255) / 256);
+  max_pool_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), h, wd, c, ho, wo, pool_h,
+      pool_w, stride_h, stride_w, same_pad_before(h, pool_h, stride_h),
+      same_pad_before(wd, pool_w, stride_w), total);
+  EDET_CHECK_LAUNCH();
+  return EDET_OK;
+}

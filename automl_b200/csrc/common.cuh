@@ -1,0 +1,103 @@
+// Shared device/host helpers for the automl_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/automl_b200.h"
+
+namespace edet {
+
+void set_error(const char* fmt, ...);
+
+#define EDET_CHECK_ARG(cond, ...)            \
+  do {                                       \
+    if (!(cond)) {                           \
+      ::edet::set_error(__VA_ARGS__);        \
+      return EDET_ERR_INVALID;               \
+    }                                        \
+  } while (0)
+
+#define EDET_CHECK_CUDA(expr)                                                        \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      ::edet::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                        __FILE__, __LINE__);                                         \
+      return EDET_ERR_CUDA;                                                          \
+    }                                                                                \
+  } while (0)
+
+#define EDET_CHECK_LAUNCH() EDET_CHECK_CUDA(cudaGetLastError())
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// TensorFlow 'SAME' padding before the first element (extra padding goes after the last).
+__host__ __device__ inline int same_pad_before(int in, int k, int s) {
+  int out = (in + s - 1) / s;
+  int total = (out - 1) * s + k - in;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+
+// Activations (utils.py:36-53 of the reference). Computed in fp32.
+// swish: x * sigmoid(x) with ex2.approx / rcp.approx (2 MUFU ops, ~1e-7 relative).
+__device__ __forceinline__ float act_swish(float x) {
+  return __fdividef(x, 1.0f + __expf(-x));
+}
+__device__ __forceinline__ float act_sigmoid(float x) {
+  return __fdividef(1.0f, 1.0f + __expf(-x));
+}
+template <int ACT>
+__device__ __forceinline__ float apply_act_t(float x) {
+  if (ACT == EDET_ACT_SWISH) return act_swish(x);
+  if (ACT == EDET_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == EDET_ACT_RELU6) return fminf(fmaxf(x, 0.f), 6.f);
+  if (ACT == EDET_ACT_HSWISH) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  if (ACT == EDET_ACT_SIGMOID) return act_sigmoid(x);
+  return x;
+}
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case EDET_ACT_SWISH: return act_swish(x);
+    case EDET_ACT_RELU: return fmaxf(x, 0.f);
+    case EDET_ACT_RELU6: return fminf(fmaxf(x, 0.f), 6.f);
+    case EDET_ACT_HSWISH: return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    case EDET_ACT_SIGMOID: return act_sigmoid(x);
+    default: return x;
+  }
+}
+
+// 8 halves <-> 8 floats through one 128-bit register quad.
+struct alignas(16) Half8 {
+  __half2 h[4];
+};
+__device__ __forceinline__ void half8_to_float(const uint4& v, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 float_to_half8(const float* f) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+inline cudaStream_t as_stream(edet_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace edet

@@ -1,0 +1,508 @@
+// Pointwise (1x1) convolution as an NHWC GEMM on the 5th-generation tensor cores (sm_100a).
+//
+//   out[b, r, n] = act( sum_k A[b, r, k] * Wt[b|0, n, k] + bias[n] ) (+ residual[b, r, n])
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      : TMA producer  -- cp.async.bulk.tensor (3-D maps, 128B swizzle) for the A tile
+//                 [128 x 64] and the W tile [block_n x 64] into an N-stage smem ring (mbarrier
+//                 complete_tx).  Out-of-bounds rows / K tail are zero-filled by TMA.
+//   warp 1      : allocates TMEM, then one lane issues tcgen05.mma (kind::f16, M=128,
+//                 N=block_n, K=16) with fp32 accumulators in TMEM, double-buffered across tiles;
+//                 tcgen05.commit releases smem stages / publishes the accumulator.
+//   warps 2..5  : epilogue -- tcgen05.ld (32x32b) -> +bias -> activation -> (+residual) -> fp16 ->
+//                 swizzled st.shared -> TMA store (cp.async.bulk.tensor ... bulk_group), which
+//                 also clips the ragged M / N edges.
+//
+// Replaces Conv2D 1x1 (+BN, +swish, +skip) at the reference call sites listed in
+// include/automl_b200.h (edet_pointwise_conv).  Algorithmic HBM bytes per launch:
+//   2*(batch*rows*k + batch*rows*nout [+ same for residual]) + 2*wbatch*nout*k   (SURVEY 8d).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace edet {
+namespace pwtc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 halves = 128 bytes = one 128B-swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kStoreStages = 2;
+constexpr int kStoreCols = 64;
+constexpr int kATileBytes = BLOCK_M * BLOCK_K * 2;        // 16 KiB
+constexpr int kStoreBytes = BLOCK_M * kStoreCols * 2;     // 16 KiB
+constexpr int kMaxStages = 8;
+constexpr int kSmemLimit = 232448;                        // 227 KiB
+
+struct Params {
+  int batch, rows, k, nout;
+  int block_n, num_m_blocks, num_n_blocks, num_k_blocks, num_stages;
+  int wbatch, ldr, tmem_cols;
+  int total_tiles;
+  const float* bias;
+  const __half* residual;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1,
+                                             int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(map)),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_barrier() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+}
+
+// K-major, 128B-swizzled smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 1024>>4 | version [46,48) = 1 |
+// layout [61,64) = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+struct TileCoord {
+  int b, m_blk, n_blk;
+};
+__device__ __forceinline__ TileCoord decode_tile(int t, const Params& p) {
+  TileCoord c;
+  c.n_blk = t % p.num_n_blocks;
+  t /= p.num_n_blocks;
+  c.m_blk = t % p.num_m_blocks;
+  c.b = t / p.num_m_blocks;
+  return c;
+}
+
+template <int ACT, bool HAS_RES>
+__global__ void __launch_bounds__(kThreads, 1)
+pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                    const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_o, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for the swizzle atoms.
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int stage_bytes = kATileBytes + p.block_n * BLOCK_K * 2;
+  uint8_t* smem_store = smem + p.num_stages * stage_bytes;
+  float* smem_bias = reinterpret_cast<float*>(smem_store + kStoreStages * kStoreBytes);  // [2][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + 2 * 256);
+  uint64_t* full_bar = bars;                       // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]
+  uint64_t* tmem_full_bar = bars + 2 * kMaxStages;     // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * kMaxStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tmem_full_bar[s]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[s]), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_o)) : "memory");
+  }
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(static_cast<uint32_t>(p.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(t, p);
+        const int wb = (p.wbatch > 1) ? tc.b : 0;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, tx_bytes);
+          uint8_t* sa = smem + stage * stage_bytes;
+          tma_load_3d(smem_u32(sa), &map_a, fb, kb * BLOCK_K, tc.m_blk * BLOCK_M, tc.b);
+          tma_load_3d(smem_u32(sa + kATileBytes), &map_w, fb, kb * BLOCK_K, tc.n_blk * p.block_n,
+                      wb);
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b F16 (0), K-major both,
+      // n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.
+      const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(p.block_n >> 3) << 17) |
+                             (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * p.block_n);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          uint8_t* sa = smem + stage * stage_bytes;
+          const uint64_t da = make_smem_desc(smem_u32(sa));
+          const uint64_t db = make_smem_desc(smem_u32(sa + kATileBytes));
+          const int k_rem = p.k - kb * BLOCK_K;
+          const int ksteps = k_rem >= BLOCK_K ? BLOCK_K / UMMA_K : (k_rem + UMMA_K - 1) / UMMA_K;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            // advance 16 halves = 32 bytes inside the swizzle atom: +2 in the >>4 address field
+            tc_mma_f16(tmem_d, da + static_cast<uint64_t>(ks * 2), db + static_cast<uint64_t>(ks * 2),
+                       idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&empty_bar[stage]));  // frees the smem stage when the MMAs retire
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(smem_u32(&tmem_full_bar[as]));  // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===================== Epilogue (warps 2..5) =====================
+    const int e_tid = threadIdx.x - 64;       // 0..127
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int row_in_tile = quarter * 32 + lane;
+    int iter = 0;
+    int store_iter = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++iter) {
+      const TileCoord tc = decode_tile(t, p);
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      const int n0 = tc.n_blk * p.block_n;
+      float* bias_s = smem_bias + as * 256;
+      for (int j = e_tid; j < p.block_n; j += kEpiThreads) {
+        const int col = n0 + j;
+        bias_s[j] = (col < p.nout) ? __ldg(p.bias + col) : 0.f;
+      }
+      const int row = tc.m_blk * BLOCK_M + row_in_tile;
+      const bool row_ok = row < p.rows;
+      const __half* res_row = nullptr;
+      if (HAS_RES) {
+        res_row = p.residual + (static_cast<size_t>(tc.b) * p.rows + (row_ok ? row : 0)) * p.ldr;
+      }
+      mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
+      tc_fence_after();
+      const int num_chunks = (p.block_n + kStoreCols - 1) / kStoreCols;
+      for (int c = 0; c < num_chunks; ++c, ++store_iter) {
+        const int cols = min(kStoreCols, p.block_n - c * kStoreCols);  // multiple of 16
+        const int sb = store_iter % kStoreStages;
+        uint8_t* stage_buf = smem_store + sb * kStoreBytes;
+        if (e_tid == 0) tma_store_wait_read<kStoreStages - 1>();
+        epi_barrier();  // staging buffer free; bias_s visible
+        float v[64];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(as * p.block_n + c * kStoreCols);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g * 16 < cols) tc_ld16(taddr + g * 16, v + g * 16);
+        }
+        tc_wait_ld();
+        if (c == num_chunks - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+        }
+        uint8_t* row_base = stage_buf + row_in_tile * 128;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          if (jj * 8 < cols) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = v[jj * 8 + e] + bias_s[c * kStoreCols + jj * 8 + e];
+              o[e] = (ACT < 0) ? x : apply_act_t<ACT>(x);
+            }
+            if (HAS_RES) {
+              const int col = n0 + c * kStoreCols + jj * 8;
+              if (row_ok && col < p.nout) {
+                float r[8];
+                half8_to_float(ldg_nc_v4(res_row + col), r);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] += r[e];
+              }
+            }
+            const uint4 packed = float_to_half8(o);
+            *reinterpret_cast<uint4*>(row_base + ((jj ^ (row_in_tile & 7)) << 4)) = packed;
+          }
+        }
+        fence_proxy_async_smem();
+        epi_barrier();
+        if (e_tid == 0) {
+          tma_store_3d(&map_o, smem_u32(stage_buf), n0 + c * kStoreCols, tc.m_blk * BLOCK_M, tc.b);
+          tma_store_commit();
+        }
+      }
+    }
+    if (e_tid == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(p.tmem_cols))
+                 : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || sym == nullptr) {
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+// 3-D half tensor [d2][d1][d0] (d0 contiguous), box [1][box1][64], 128B swizzle.
+static int make_map(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
+                    uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return EDET_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(BLOCK_K), box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) dims=[%llu,%llu,%llu] strides=[%llu,%llu] box1=%u",
+              static_cast<int>(r), (unsigned long long)d0, (unsigned long long)d1,
+              (unsigned long long)d2, (unsigned long long)strides[0],
+              (unsigned long long)strides[1], box1);
+    return EDET_ERR_CUDA;
+  }
+  return EDET_OK;
+}
+
+static int pick_block_n(int nout) {
+  if (nout <= 256) return ((nout + 15) / 16) * 16;
+  int best = 256, best_cost = 1 << 30;
+  for (int bn = 256; bn >= 64; bn -= 64) {
+    const int tiles = (nout + bn - 1) / bn;
+    const int cost = tiles * bn + 16 * tiles;
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+template <int ACT, bool HAS_RES>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo,
+                  const Params& p, int grid, int smem_bytes, cudaStream_t stream) {
+  auto kern = pointwise_tc_kernel<ACT, HAS_RES>;
+  static int configured_smem = 0;  // per instantiation; avoids API calls inside graph capture
+  if (smem_bytes > configured_smem) {
+    EDET_CHECK_CUDA(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    configured_smem = kSmemLimit;
+  }
+  kern<<<grid, kThreads, smem_bytes, stream>>>(ma, mw, mo, p);
+  EDET_CHECK_LAUNCH();
+  return EDET_OK;
+}
+
+int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bias,
+        const __half* residual, int ldr, __half* out, int ldo, int batch, int rows, int k, int nout,
+        int act, cudaStream_t stream) {
+  Params p;
+  p.batch = batch;
+  p.rows = rows;
+  p.k = k;
+  p.nout = nout;
+  p.block_n = pick_block_n(nout);
+  p.num_m_blocks = ceil_div(rows, BLOCK_M);
+  p.num_n_blocks = ceil_div(nout, p.block_n);
+  p.num_k_blocks = ceil_div(k, BLOCK_K);
+  p.wbatch = wbatch;
+  p.ldr = ldr;
+  p.bias = bias;
+  p.residual = residual;
+  int cols = 32;
+  while (cols < 2 * p.block_n) cols *= 2;
+  p.tmem_cols = cols;
+  p.total_tiles = batch * p.num_m_blocks * p.num_n_blocks;
+
+  const int stage_bytes = kATileBytes + p.block_n * BLOCK_K * 2;
+  const int fixed = kStoreStages * kStoreBytes + 2 * 256 * 4 + (2 * kMaxStages + 4) * 8 + 16;
+  int stages = (kSmemLimit - 1024 - fixed) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  EDET_CHECK_ARG(stages >= 2, "pointwise_tc: block_n %d leaves <2 pipeline stages", p.block_n);
+  p.num_stages = stages;
+  const int smem_bytes = 1024 + stages * stage_bytes + fixed;
+
+  CUtensorMap ma, mw, mo;
+  int rc;
+  if ((rc = make_map(&ma, a, k, rows, batch, lda, static_cast<uint64_t>(rows) * lda, BLOCK_M)))
+    return rc;
+  if ((rc = make_map(&mw, wt, k, nout, wbatch, k, static_cast<uint64_t>(nout) * k, p.block_n)))
+    return rc;
+  if ((rc = make_map(&mo, out, nout, rows, batch, ldo, static_cast<uint64_t>(rows) * ldo, BLOCK_M)))
+    return rc;
+
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    EDET_CHECK_CUDA(cudaGetDevice(&dev));
+    EDET_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = p.total_tiles < sm_count ? p.total_tiles : sm_count;
+  const bool has_res = residual != nullptr;
+
+#define EDET_PW_CASE(A)                                                              \
+  return has_res ? launch<A, true>(ma, mw, mo, p, grid, smem_bytes, stream)          \
+                 : launch<A, false>(ma, mw, mo, p, grid, smem_bytes, stream)
+  switch (act) {
+    case EDET_ACT_NONE: EDET_PW_CASE(EDET_ACT_NONE);
+    case EDET_ACT_SWISH: EDET_PW_CASE(EDET_ACT_SWISH);
+    case EDET_ACT_RELU: EDET_PW_CASE(EDET_ACT_RELU);
+    case EDET_ACT_RELU6: EDET_PW_CASE(EDET_ACT_RELU6);
+    case EDET_ACT_HSWISH: EDET_PW_CASE(EDET_ACT_HSWISH);
+    case EDET_ACT_SIGMOID: EDET_PW_CASE(EDET_ACT_SIGMOID);
+    default:
+      set_error("pointwise_tc: bad activation %d", act);
+      return EDET_ERR_INVALID;
+  }
+#undef EDET_PW_CASE
+}
+
+}  // namespace pwtc
+}  // namespace edet

@@ -1,0 +1,429 @@
+"""Lowers a resolved EfficientDet architecture to a static list of kernel launches on one B200.
+
+  * folds inference BatchNorm into the conv weights (reference utils.py:244-326, eps 1e-3),
+    casts weights to fp16 / biases to fp32 and uploads them once;
+  * allocates every activation buffer once (NHWC fp16, static shapes);
+  * records the launch list (stem -> MBConv blocks -> extra levels -> BiFPN cells -> heads ->
+    pre-NMS -> NMS) and replays it, optionally as one CUDA graph.
+
+The launch list mirrors the call structure of efficientdet_arch.efficientdet
+(/root/reference/efficientdet/efficientdet_arch.py:547-577) and inference.det_post_process
+(inference.py:233-271).  PyTorch is used for device memory, streams and graph capture only.
+"""
+import math
+
+import numpy as np
+import torch
+
+from automl_b200 import anchors as anchors_lib
+from automl_b200 import ops
+from automl_b200 import utils
+from automl_b200.arch import DetArch
+
+
+def _round_up(x, m):
+  return (x + m - 1) // m * m
+
+
+def _bn_fold(w, scope, eps):
+  """(scale, shift) float64 for y = x*scale + shift."""
+  g = np.asarray(w[scope + '/gamma'], np.float64)
+  b = np.asarray(w[scope + '/beta'], np.float64)
+  m = np.asarray(w[scope + '/moving_mean'], np.float64)
+  v = np.asarray(w[scope + '/moving_variance'], np.float64)
+  scale = g / np.sqrt(v + eps)
+  return scale, b - m * scale
+
+
+def nms_v5_params(nms_configs):
+  """(iou_thresh, score_thresh, tf_sigma) as postprocess.nms passes them to
+  NonMaxSuppressionV5 (tf2/postprocess.py:175-199)."""
+  method = nms_configs['method']
+  if method == 'hard' or not method:
+    sigma = 0.0
+    iou_thresh = nms_configs['iou_thresh'] or 0.5
+    score_thresh = nms_configs['score_thresh'] or float('-inf')
+  elif method == 'gaussian':
+    sigma = nms_configs['sigma'] or 0.5
+    iou_thresh = 0.5
+    score_thresh = nms_configs['score_thresh'] or 0.001
+  else:
+    raise ValueError('Inference has invalid nms method {}'.format(method))
+  return iou_thresh, score_thresh, sigma / 2
+
+
+class Engine(object):
+  """One network instance bound to one device, one batch size and one image size."""
+
+  def __init__(self, config, weights, batch_size, device='cuda:0', pw_impl=ops.PW_TCGEN05,
+               use_cuda_graph=True, image_id_base=0):
+    if not torch.cuda.is_available():
+      raise RuntimeError('automl_b200.Engine needs a CUDA device; there is no CPU fallback')
+    self.config = config
+    self.arch = a = DetArch(config)
+    self.n = int(batch_size)
+    self.device = torch.device(device)
+    self.pw_impl = pw_impl
+    self.use_cuda_graph = use_cuda_graph
+    self.image_id_base = image_id_base
+    self.act = utils.activation_code(a.act_type)
+    self._graph = None
+    self._ops = []          # (name, callable)
+    self.op_info = []       # parallel to _ops: kind / algorithmic bytes / flops
+    self.buffers = {}       # debug / tests: name -> tensor
+    self._keep = []         # keeps weight tensors alive
+    self.launches_per_forward = 0
+    with torch.cuda.device(self.device):
+      self._build(weights)
+
+  # ---- helpers --------------------------------------------------------------------------
+  def _dev(self, arr, dtype):
+    t = torch.as_tensor(np.ascontiguousarray(arr)).to(dtype).to(self.device).contiguous()
+    self._keep.append(t)
+    return t
+
+  def _buf(self, name, shape, dtype=torch.float16):
+    t = torch.empty(shape, dtype=dtype, device=self.device)
+    self.buffers[name] = t
+    return t
+
+  def _add(self, name, fn, kind='other', nbytes=0, flops=0):
+    """kind groups launches of the same kernel; nbytes / flops are the ALGORITHMIC HBM bytes
+    and floating-point operations of the launch (SURVEY.md 8d formulas), used by bench.py."""
+    self._ops.append((name, fn))
+    self.op_info.append({'name': name, 'kind': kind, 'bytes': int(nbytes), 'flops': int(flops)})
+
+  def _pw(self, name, a, wt, bias, out, act, residual=None, batch=1, rows=None, nout=None):
+    if rows is None:
+      rows = a.numel() // (a.shape[-1] * batch)
+    impl = self.pw_impl
+    k = wt.shape[-1]
+    n_out = nout if nout is not None else wt.shape[-2]
+    m = rows * batch
+    wbatch = wt.shape[0] if wt.dim() == 3 else 1
+    nbytes = 2 * (m * k + m * n_out * (2 if residual is not None else 1)) + 2 * wbatch * n_out * k
+    self._add(name, lambda: ops.pointwise_conv(a, wt, bias, out, act, residual=residual,
+                                               rows=rows, batch=batch, nout=nout, impl=impl),
+              kind='pointwise_tc' if impl == ops.PW_TCGEN05 else 'pointwise_simt',
+              nbytes=nbytes, flops=2 * m * k * n_out)
+
+  # ---- network lowering -------------------------------------------------------------------
+  def _build(self, w):
+    a, n, act = self.arch, self.n, self.act
+    eps = a.bn_eps
+    f16, f32 = torch.float16, torch.float32
+    H, W = a.image_hw
+    self.input = self._buf('input', (n, H, W, 3), f32)
+
+    def check_c(c, what):
+      if c % 8:
+        raise NotImplementedError('%s has %d channels; the kernels need multiples of 8' % (what, c))
+
+    # -- stem ---------------------------------------------------------------------------------
+    bb = a.backbone_name
+    scale, shift = _bn_fold(w, bb + '/stem/tpu_batch_normalization', eps)
+    k = np.asarray(w[bb + '/stem/conv2d/kernel'], np.float64) * scale  # [3,3,3,C]
+    stem_w = self._dev(k.reshape(27, -1), f16)
+    stem_b = self._dev(shift, f32)
+    h, wd = a.level_hw[1]
+    x = self._buf('stem', (n, h, wd, a.stem_filters))
+    inp = self.input
+    self._add('stem', lambda inp=inp, x=x: ops.stem_conv(inp, x, stem_w, stem_b, act),
+              kind='stem', nbytes=12 * n * H * W + 2 * n * h * wd * a.stem_filters,
+              flops=2 * 27 * n * h * wd * a.stem_filters)
+    cur, cur_hw = x, (h, wd)
+
+    # -- MBConv blocks ----------------------------------------------------------------------
+    feats = {}
+    for b in a.blocks:
+      scope = '%s/%s' % (bb, b.name)
+      check_c(b.input_filters, scope); check_c(b.mid_filters, scope); check_c(b.output_filters, scope)
+      h, wd = cur_hw
+      x_in = cur
+      mid = x_in
+      if b.expand_name:
+        s, sh = _bn_fold(w, '%s/%s' % (scope, b.expand_bn), eps)
+        kw = np.asarray(w['%s/%s/kernel' % (scope, b.expand_name)], np.float64)[0, 0]  # [Cin,Cmid]
+        wt = self._dev((kw * s).T, f16)
+        bias = self._dev(sh, f32)
+        mid = self._buf(b.name + '/expand', (n, h, wd, b.mid_filters))
+        self._pw(b.name + '/expand', x_in, wt, bias, mid, act)
+      # depthwise
+      s, sh = _bn_fold(w, '%s/%s' % (scope, b.dw_bn), eps)
+      kd = np.asarray(w[scope + '/depthwise_conv2d/depthwise_kernel'], np.float64)[..., 0]  # [k,k,C]
+      dw_w = self._dev((kd * s).reshape(b.kernel_size * b.kernel_size, -1), f16)
+      dw_b = self._dev(sh, f32)
+      ho, wo = utils.same_pad(h, b.kernel_size, b.stride)[0], utils.same_pad(wd, b.kernel_size, b.stride)[0]
+      dwo = self._buf(b.name + '/dw', (n, ho, wo, b.mid_filters))
+      partial = None
+      if b.se_filters:
+        tiles = ops.depthwise_tiles(h, wd, b.mid_filters, b.kernel_size, b.stride)
+        partial = self._buf(b.name + '/se_partial', (n, tiles, b.mid_filters), f32)
+      self._add(b.name + '/dw',
+                lambda mid=mid, dwo=dwo, dw_w=dw_w, dw_b=dw_b, partial=partial, b=b:
+                ops.depthwise_conv(mid, dwo, dw_w, dw_b, act, b.kernel_size, b.stride, partial),
+                kind='depthwise_k%ds%d' % (b.kernel_size, b.stride),
+                nbytes=2 * n * b.mid_filters * (h * wd + ho * wo) + 2 * b.kernel_size**2 * b.mid_filters
+                + (4 * partial.numel() if partial is not None else 0),
+                flops=2 * b.kernel_size**2 * n * b.mid_filters * ho * wo)
+      # project (+SE folded into per-image weights, + skip)
+      s, sh = _bn_fold(w, '%s/%s' % (scope, b.project_bn), eps)
+      kp = np.asarray(w['%s/%s/kernel' % (scope, b.project_name)], np.float64)[0, 0]  # [Cmid,Cout]
+      proj_wt = self._dev((kp * s).T, f16)  # [Cout, Cmid]
+      proj_b = self._dev(sh, f32)
+      y = self._buf(b.name + '/out', (n, ho, wo, b.output_filters))
+      res = x_in if b.has_skip else None
+      if b.se_filters:
+        w1 = self._dev(np.asarray(w[scope + '/se/conv2d/kernel'], np.float64)[0, 0].T, f32)   # [se,C]
+        b1 = self._dev(w[scope + '/se/conv2d/bias'], f32)
+        w2 = self._dev(np.asarray(w[scope + '/se/conv2d_1/kernel'], np.float64)[0, 0].T, f32)  # [C,se]
+        b2 = self._dev(w[scope + '/se/conv2d_1/bias'], f32)
+        gate = self._buf(b.name + '/se_gate', (n, b.mid_filters), f32)
+        wt_scaled = self._buf(b.name + '/proj_w', (n, b.output_filters, b.mid_filters))
+        inv_hw = 1.0 / float(ho * wo)
+        self._add(b.name + '/se',
+                  lambda partial=partial, inv_hw=inv_hw, w1=w1, b1=b1, w2=w2, b2=b2, gate=gate,
+                  proj_wt=proj_wt, wt_scaled=wt_scaled:
+                  ops.se_fc(partial, inv_hw, w1, b1, w2, b2, gate, act, proj_wt, wt_scaled),
+                  kind='se_fc', nbytes=4 * partial.numel() + 2 * proj_wt.numel() + 2 * wt_scaled.numel())
+        self._pw(b.name + '/project', dwo, wt_scaled, proj_b, y, utils.ACT_NONE, residual=res,
+                 batch=n, rows=ho * wo)
+      else:
+        self._pw(b.name + '/project', dwo, proj_wt, proj_b, y, utils.ACT_NONE, residual=res)
+      cur, cur_hw = y, (ho, wo)
+      if b.reduction:
+        feats[b.reduction] = y
+
+    # -- feature network --------------------------------------------------------------------
+    F = a.fpn_filters
+    check_c(F, 'fpn_num_filters')
+
+    def resample_conv(r, src):
+      """1x1 conv(+bias)+BN of a resample op at the SOURCE resolution (conv_after_downsample
+      is False for every registered model)."""
+      kw = np.asarray(w[r.scope + '/conv2d/kernel'], np.float64)[0, 0]  # [Cin,F]
+      cb = np.asarray(w[r.scope + '/conv2d/bias'], np.float64)
+      if a.config.apply_bn_for_resampling:
+        s, sh = _bn_fold(w, r.scope + '/bn', eps)
+      else:
+        s, sh = np.ones(F), np.zeros(F)
+      wt = self._dev((kw * s).T, f16)
+      bias = self._dev(cb * s + sh, f32)
+      out = self._buf(r.scope + '/conv', (n, r.in_hw[0], r.in_hw[1], F))
+      self._pw(r.scope + '/conv', src, wt, bias, out, utils.ACT_NONE)
+      return out
+
+    pyramid = []
+    for level, _ in a.pyramid_in:
+      if level in feats:
+        pyramid.append(feats[level])
+    for r in a.extra_levels:
+      src = pyramid[r.src]
+      if r.has_conv:
+        src = resample_conv(r, src)
+      out = self._buf(r.scope, (n, r.out_hw[0], r.out_hw[1], F))
+      if r.mode != 'down':
+        raise NotImplementedError('extra level that is not a downsample')
+      self._add(r.scope + '/pool',
+                lambda src=src, out=out, r=r: ops.max_pool(src, out, r.pool[:2], r.pool[2:]),
+                kind='max_pool', nbytes=2 * (src.numel() + out.numel()))
+      pyramid.append(out)
+
+    mode_code = {'same': ops.RS_SAME, 'up': ops.RS_UP, 'down': ops.RS_DOWN}
+    for ci, cell in enumerate(a.cells):
+      cell_feats = list(pyramid)
+      for node in cell['nodes']:
+        specs = []
+        # fusion weights (efficientdet_arch.py:439-447), float32 like the reference
+        if a.fpn_weight_method == 'fastattn':
+          ew = [np.maximum(np.float32(w['%s/WSM%s' % (node.scope, '' if i == 0 else '_%d' % i)]),
+                           np.float32(0)) for i in range(len(node.inputs))]
+          tot = np.float32(sum(ew)) + np.float32(0.0001)
+          fw = [np.float32(e) / tot for e in ew]
+        elif a.fpn_weight_method == 'attn':
+          ev = np.asarray([np.float32(w['%s/WSM%s' % (node.scope, '' if i == 0 else '_%d' % i)])
+                           for i in range(len(node.inputs))], np.float32)
+          ex = np.exp(ev - ev.max())
+          fw = list(ex / ex.sum())
+        elif a.fpn_weight_method == 'sum':
+          fw = [1.0] * len(node.inputs)
+        else:
+          raise NotImplementedError('fpn_weight_method %s' % a.fpn_weight_method)
+        for r, wgt in zip(node.inputs, fw):
+          src = cell_feats[r.src]
+          if r.has_conv:
+            src = resample_conv(r, src)
+          specs.append((src, mode_code[r.mode], r.pool, float(wgt)))
+        op = node.op_scope
+        dw_w = self._dev(np.asarray(w[op + '/conv/depthwise_kernel'], np.float64)[..., 0].reshape(9, F), f16)
+        s, sh = _bn_fold(w, op + '/bn', eps)
+        kp = np.asarray(w[op + '/conv/pointwise_kernel'], np.float64)[0, 0]
+        cb = np.asarray(w[op + '/conv/bias'], np.float64)
+        pw_wt = self._dev((kp * s).T, f16)
+        pw_b = self._dev(cb * s + sh, f32)
+        hh, ww = node.hw
+        tmp = self._buf(node.scope + '/fused_dw', (n, hh, ww, F))
+        out = self._buf(node.scope + '/out', (n, hh, ww, F))
+        self._add(node.scope + '/fuse_dw',
+                  lambda specs=specs, dw_w=dw_w, tmp=tmp: ops.fuse_dw(specs, dw_w, tmp, act),
+                  kind='bifpn_fuse_dw',
+                  nbytes=2 * (sum(sp[0].numel() for sp in specs) + tmp.numel()) + 18 * F,
+                  flops=2 * 9 * tmp.numel())
+        self._pw(node.scope + '/pw', tmp, pw_wt, pw_b, out, utils.ACT_NONE)
+        cell_feats.append(out)
+      pyramid = [cell_feats[cell['out_index'][l]] for l in a.levels]
+    self.fpn_feats = dict(zip(a.levels, pyramid))
+
+    # -- heads ----------------------------------------------------------------------------------
+    A, C = a.num_anchors, a.num_classes
+    self.ld_cls, self.ld_box = _round_up(A * C, 8), _round_up(A * 4, 8)
+    self.cls_out, self.box_out = {}, {}
+    for net, pred_c, ld in (('class', A * C, self.ld_cls), ('box', A * 4, self.ld_box)):
+      scope = '%s_net' % net
+      dws, pws, pbs = [], [], []
+      for i in range(a.head_repeats):
+        name = '%s/%s-%d' % (scope, net, i)
+        dws.append(self._dev(np.asarray(w[name + '/depthwise_kernel'], np.float64)[..., 0].reshape(9, F), f16))
+        pws.append(np.asarray(w[name + '/pointwise_kernel'], np.float64)[0, 0])
+        pbs.append(np.asarray(w[name + '/bias'], np.float64))
+      name = '%s/%s-predict' % (scope, net)
+      pred_dw = self._dev(np.asarray(w[name + '/depthwise_kernel'], np.float64)[..., 0].reshape(9, F), f16)
+      pred_wt = self._dev(np.asarray(w[name + '/pointwise_kernel'], np.float64)[0, 0].T, f16)  # [pred_c, F]
+      pred_b = self._dev(w[name + '/bias'], f32)
+      for level in a.levels:
+        hh, ww = a.level_hw[level]
+        x = self.fpn_feats[level]
+        t = self._buf('%s/l%d/t' % (scope, level), (n, hh, ww, F))
+        ping = self._buf('%s/l%d/a' % (scope, level), (n, hh, ww, F))
+        pong = self._buf('%s/l%d/b' % (scope, level), (n, hh, ww, F))
+        for i in range(a.head_repeats):
+          s, sh = _bn_fold(w, '%s/%s-%d-bn-%d' % (scope, net, i, level), eps)
+          wt = self._dev((pws[i] * s).T, f16)
+          bias = self._dev(pbs[i] * s + sh, f32)
+          y = ping if i % 2 == 0 else pong
+          self._add('%s/l%d/dw%d' % (scope, level, i),
+                    lambda x=x, t=t, dwk=dws[i]: ops.depthwise_conv(x, t, dwk, None, utils.ACT_NONE, 3, 1),
+                    kind='depthwise_k3s1', nbytes=4 * t.numel() + 18 * F, flops=18 * t.numel())
+          self._pw('%s/l%d/pw%d' % (scope, level, i), t, wt, bias, y, act)
+          x = y
+        out = self._buf('%s/l%d/out' % (scope, level), (n, hh, ww, ld))
+        out.zero_()
+        self._add('%s/l%d/dwp' % (scope, level),
+                  lambda x=x, t=t, pred_dw=pred_dw: ops.depthwise_conv(x, t, pred_dw, None, utils.ACT_NONE, 3, 1),
+                  kind='depthwise_k3s1', nbytes=4 * t.numel() + 18 * F, flops=18 * t.numel())
+        self._pw('%s/l%d/predict' % (scope, level), t, pred_wt, pred_b, out, utils.ACT_NONE,
+                 nout=pred_c)
+        (self.cls_out if net == 'class' else self.box_out)[level] = out
+    self.num_network_ops = len(self._ops)
+
+    # -- post-processing ----------------------------------------------------------------------
+    p = a.config
+    self.anchors = anchors_lib.Anchors(p.min_level, p.max_level, p.num_scales,
+                                       list(p.aspect_ratios), p.anchor_scale, p.image_size)
+    anc = self._dev(self.anchors.boxes, f32)
+    K = self.anchors.boxes.shape[0]
+    self.total_anchors = K
+    nms_cfg = p.nms_configs.as_dict() if hasattr(p.nms_configs, 'as_dict') else dict(p.nms_configs)
+    iou_t, score_t, tf_sigma = nms_v5_params(nms_cfg)
+    self.max_output_size = int(nms_cfg['max_output_size'])
+    self.boxes = self._buf('boxes', (n, K, 4), f32)
+    self.scores = self._buf('scores', (n, K), f32)
+    self.classes = self._buf('classes', (n, K), torch.int32)
+    self.image_scales = self._buf('image_scales', (n,), f32)
+    self.image_scales.fill_(1.0)
+    self.detections = self._buf('detections', (n, self.max_output_size, 7), f32)
+    self.sel_index = self._buf('sel_index', (n, self.max_output_size), torch.int32)
+    self.valid = self._buf('valid', (n,), torch.int32)
+    work = self._buf('nms_work', (ops.nms_work_bytes(n, K),), torch.uint8)
+    cls_l = [self.cls_out[l] for l in a.levels]
+    box_l = [self.box_out[l] for l in a.levels]
+    level_hw = [a.level_hw[l] for l in a.levels]
+    self._add('pre_nms', lambda: ops.pre_nms(cls_l, box_l, level_hw, A, C, anc, self.boxes,
+                                            self.scores, self.classes),
+              kind='pre_nms',
+              nbytes=2 * sum(t.numel() for t in cls_l + box_l) + 24 * n * K + 16 * K)
+    self._add('nms', lambda: ops.nms_v5(self.boxes, self.scores, self.classes, self.image_scales,
+                                       self.image_id_base, self.max_output_size, iou_t, score_t,
+                                       tf_sigma, (float(H), float(W)), self.detections,
+                                       self.sel_index, self.valid, work),
+              kind='nms_v5', nbytes=28 * n * K)
+    self.launches_per_forward = len(self._ops)
+
+  # ---- execution ------------------------------------------------------------------------------
+  def _run_ops(self, upto=None):
+    for _, fn in (self._ops if upto is None else self._ops[:upto]):
+      fn()
+
+  def run(self, postprocess=True):
+    """Enqueues one forward (+post-process) on the current stream, from self.input."""
+    upto = None if postprocess else self.num_network_ops
+    if not self.use_cuda_graph:
+      self._run_ops(upto)
+      return
+    key = bool(postprocess)
+    if self._graph is None:
+      self._graph = {}
+    if key not in self._graph:
+      # warm-up outside capture (sets kernel attributes, loads modules), then capture
+      self._run_ops(upto)
+      torch.cuda.synchronize(self.device)
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g):
+        self._run_ops(upto)
+      self._graph[key] = g
+    self._graph[key].replay()
+
+  def set_input(self, images):
+    """images: float32 [N,H,W,3] tensor (any device) or array; copied into the static input."""
+    t = torch.as_tensor(images)
+    if tuple(t.shape) != tuple(self.input.shape):
+      raise ValueError('expected input shape %s, got %s' % (tuple(self.input.shape), tuple(t.shape)))
+    self.input.copy_(t.to(torch.float32), non_blocking=True)
+
+  def forward(self, images=None):
+    """Network only: returns (cls_outputs, box_outputs) dicts level -> fp16 views
+    [N,H_l,W_l,A*C] / [N,H_l,W_l,4A] (strided views into padded buffers)."""
+    with torch.cuda.device(self.device):
+      if images is not None:
+        self.set_input(images)
+      self.run(postprocess=False)
+    A, C = self.arch.num_anchors, self.arch.num_classes
+    return ({l: t[..., :A * C] for l, t in self.cls_out.items()},
+            {l: t[..., :A * 4] for l, t in self.box_out.items()})
+
+  def detect(self, images=None, image_scales=None):
+    """Network + post-process: float32 [N, max_output_size, 7] device tensor."""
+    with torch.cuda.device(self.device):
+      if images is not None:
+        self.set_input(images)
+      if image_scales is not None:
+        self.image_scales.copy_(torch.as_tensor(image_scales, dtype=torch.float32), non_blocking=True)
+      self.run(postprocess=True)
+    return self.detections
+
+  def op_names(self):
+    return [n for n, _ in self._ops]
+
+  def profile_ops(self, iters=3, postprocess=True):
+    """Times every launch of the list individually with CUDA events on the current stream
+    (eager launches, not the graph) and returns op_info rows extended with 'ms' (mean)."""
+    upto = len(self._ops) if postprocess else self.num_network_ops
+    with torch.cuda.device(self.device):
+      self._run_ops(upto)  # warm-up
+      torch.cuda.synchronize()
+      acc = [0.0] * upto
+      for _ in range(iters):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(upto + 1)]
+        evs[0].record()
+        for i in range(upto):
+          self._ops[i][1]()
+          evs[i + 1].record()
+        torch.cuda.synchronize()
+        for i in range(upto):
+          acc[i] += evs[i].elapsed_time(evs[i + 1])
+    rows = []
+    for i in range(upto):
+      r = dict(self.op_info[i])
+      r['ms'] = acc[i] / iters
+      rows.append(r)
+    return rows

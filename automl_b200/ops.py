@@ -1,0 +1,133 @@
+"""Tensor-level wrappers over the C-ABI (torch tensors are only device-memory containers).
+
+Every function enqueues on the CURRENT torch CUDA stream, allocates nothing except where
+stated, and raises if the tensors are not CUDA / not contiguous / misaligned.  There is no CPU
+implementation behind any of them.
+"""
+import ctypes
+
+import torch
+
+from automl_b200 import _lib
+from automl_b200._lib import FuseInput, PW_SIMT, PW_TCGEN05, RS_DOWN, RS_SAME, RS_UP  # noqa: F401
+
+
+def _stream():
+  return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=None):
+  if t is None:
+    return None
+  if not t.is_cuda:
+    raise ValueError('automl_b200 ops need CUDA tensors (no CPU fallback)')
+  if dtype is not None and t.dtype != dtype:
+    raise ValueError('expected %s, got %s' % (dtype, t.dtype))
+  if not t.is_contiguous():
+    raise ValueError('tensor must be contiguous')
+  return ctypes.c_void_p(t.data_ptr())
+
+
+def stem_conv(images, out, w, bias, act):
+  """images fp32 [N,H,W,3] -> out fp16 [N,ceil(H/2),ceil(W/2),C]."""
+  n, h, wd, c3 = images.shape
+  assert c3 == 3
+  _lib.call('edet_stem_conv', _ptr(images, torch.float32), _ptr(out, torch.float16),
+            _ptr(w, torch.float16), _ptr(bias, torch.float32), n, h, wd, out.shape[-1], act,
+            _stream())
+
+
+def pointwise_conv(a, wt, bias, out, act, residual=None, rows=None, batch=None, nout=None,
+                   impl=PW_TCGEN05):
+  """a fp16 [batch, rows, lda] (k = wt.shape[-1] <= lda), wt fp16 [wbatch, nout, k] or [nout, k],
+  out fp16 [batch, rows, ldo]."""
+  k = wt.shape[-1]
+  wbatch = wt.shape[0] if wt.dim() == 3 else 1
+  n_out = nout if nout is not None else wt.shape[-2]
+  lda, ldo = a.shape[-1], out.shape[-1]
+  if batch is None:
+    batch = 1
+  if rows is None:
+    rows = a.numel() // (lda * batch)
+  ldr = residual.shape[-1] if residual is not None else 0
+  _lib.call('edet_pointwise_conv', _ptr(a, torch.float16), lda, _ptr(wt, torch.float16), wbatch,
+            _ptr(bias, torch.float32), _ptr(residual, torch.float16), ldr,
+            _ptr(out, torch.float16), ldo, batch, rows, k, n_out, act, impl, _stream())
+
+
+def depthwise_tiles(h, w, c, k, stride):
+  return _lib.load().edet_depthwise_tiles(h, w, c, k, stride)
+
+
+def depthwise_conv(x, out, w, bias, act, k, stride, se_partial=None):
+  n, h, wd, c = x.shape
+  _lib.call('edet_depthwise_conv', _ptr(x, torch.float16), _ptr(out, torch.float16),
+            _ptr(w, torch.float16), _ptr(bias, torch.float32), _ptr(se_partial, torch.float32),
+            n, h, wd, c, k, stride, act, _stream())
+
+
+def se_fc(partial, inv_hw, w1, b1, w2, b2, gate, act, wt=None, wt_scaled=None):
+  n, tiles, c = partial.shape
+  se = w1.shape[0]
+  nout = wt.shape[0] if wt is not None else 0
+  _lib.call('edet_se_fc', _ptr(partial, torch.float32), tiles, ctypes.c_float(inv_hw),
+            _ptr(w1, torch.float32), _ptr(b1, torch.float32), _ptr(w2, torch.float32),
+            _ptr(b2, torch.float32), _ptr(gate, torch.float32), _ptr(wt, torch.float16),
+            _ptr(wt_scaled, torch.float16), n, c, se, nout, act, _stream())
+
+
+def make_fuse_inputs(specs):
+  """specs: list of (tensor [N,h,w,C], mode, pool(4-tuple or None), weight)."""
+  arr = (FuseInput * len(specs))()
+  for i, (t, mode, pool, weight) in enumerate(specs):
+    arr[i].ptr = t.data_ptr()
+    arr[i].h, arr[i].w = t.shape[1], t.shape[2]
+    arr[i].mode = mode
+    ph, pw, sh, sw = pool if pool else (1, 1, 1, 1)
+    arr[i].pool_h, arr[i].pool_w, arr[i].stride_h, arr[i].stride_w = ph, pw, sh, sw
+    arr[i].weight = float(weight)
+  return arr
+
+
+def fuse_dw(specs, dw_w, out, act):
+  n, h, wd, c = out.shape
+  for t, _, _, _ in specs:
+    _ptr(t, torch.float16)
+  arr = make_fuse_inputs(specs)
+  _lib.call('edet_fuse_dw', arr, len(specs), _ptr(dw_w, torch.float16),
+            _ptr(out, torch.float16), n, h, wd, c, act, _stream())
+
+
+def max_pool(x, out, pool, stride):
+  n, h, wd, c = x.shape
+  _lib.call('edet_max_pool', _ptr(x, torch.float16), _ptr(out, torch.float16), n, h, wd, c,
+            pool[0], pool[1], stride[0], stride[1], _stream())
+
+
+def pre_nms(cls_levels, box_levels, level_hw, num_anchors, num_classes, anchors, boxes, scores,
+            classes):
+  """cls_levels[l] fp16 [N,H_l,W_l,ld_cls]; boxes fp32 [N,A,4], scores fp32 [N,A], classes i32."""
+  levels = len(cls_levels)
+  n = cls_levels[0].shape[0]
+  ld_cls, ld_box = cls_levels[0].shape[-1], box_levels[0].shape[-1]
+  cls_p = (ctypes.c_void_p * levels)(*[_ptr(t, torch.float16).value for t in cls_levels])
+  box_p = (ctypes.c_void_p * levels)(*[_ptr(t, torch.float16).value for t in box_levels])
+  hw = (ctypes.c_int * (2 * levels))(*[v for pair in level_hw for v in pair])
+  _lib.call('edet_pre_nms', cls_p, box_p, hw, levels, ld_cls, ld_box, num_anchors, num_classes,
+            _ptr(anchors, torch.float32), _ptr(boxes, torch.float32),
+            _ptr(scores, torch.float32), _ptr(classes, torch.int32), n, _stream())
+
+
+def nms_work_bytes(n, k):
+  return _lib.load().edet_nms_work_bytes(n, k)
+
+
+def nms_v5(boxes, scores, classes, image_scales, image_id_base, max_output_size, iou_threshold,
+           score_threshold, soft_nms_sigma, clip_hw, detections, sel_index, valid, work):
+  n, k = scores.shape
+  _lib.call('edet_nms_v5', _ptr(boxes, torch.float32), _ptr(scores, torch.float32),
+            _ptr(classes, torch.int32), _ptr(image_scales, torch.float32), image_id_base, n, k,
+            max_output_size, ctypes.c_float(iou_threshold), ctypes.c_float(score_threshold),
+            ctypes.c_float(soft_nms_sigma), ctypes.c_float(clip_hw[0]),
+            ctypes.c_float(clip_hw[1]), _ptr(detections, torch.float32),
+            _ptr(sel_index, torch.int32), _ptr(valid, torch.int32), _ptr(work), _stream())

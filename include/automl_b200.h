@@ -1,0 +1,178 @@
+/*
+ * automl_b200 C ABI: the sm_100a kernels behind the EfficientDet forward path.
+ *
+ * The reference (google/automl, /root/reference/efficientdet) has no plugin / FFI layer: its
+ * hot path bottoms out in TensorFlow ops.  Each entry point below replaces the TF op(s) a
+ * reference function dispatches, cited as file:line under /root/reference/efficientdet.  A
+ * reference maintainer binds them with ctypes from the same Python call
+ * sites.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name starts with `h_`;
+ *   - activations are NHWC IEEE half (`uint16_t` storage), channel counts multiples of 8,
+ *     pixel stride (`ld*`) in elements, multiple of 8 (16-byte rows for TMA / 128-bit access);
+ *   - folded inference BatchNorm: weights already carry gamma/sqrt(var+eps), `bias` is
+ *     beta - mean*scale (+ conv bias) in float32;
+ *   - the caller owns all memory (no allocation, no ownership transfer in the library);
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t) and is CUDA-graph capturable;
+ *   - return value 0 = ok, otherwise an EDET_ERR_* code; edet_last_error() gives the text.
+ *     No exceptions cross the boundary.
+ */
+#ifndef AUTOML_B200_H_
+#define AUTOML_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* edet_stream_t; /* cudaStream_t */
+typedef uint16_t edet_half;  /* IEEE binary16 bits */
+
+enum {
+  EDET_OK = 0,
+  EDET_ERR_INVALID = 1,   /* bad argument (shape / alignment / enum) */
+  EDET_ERR_CUDA = 2,      /* a CUDA runtime / driver call failed */
+  EDET_ERR_UNSUPPORTED = 3
+};
+
+/* utils.py:36-53 activation_fn; codes shared with automl_b200/utils.py */
+enum {
+  EDET_ACT_NONE = 0,
+  EDET_ACT_SWISH = 1,
+  EDET_ACT_RELU = 2,
+  EDET_ACT_RELU6 = 3,
+  EDET_ACT_HSWISH = 4,
+  EDET_ACT_SIGMOID = 5
+};
+
+/* Pointwise implementation selector. */
+enum {
+  EDET_PW_TCGEN05 = 0, /* TMA -> smem -> tcgen05.mma -> TMEM -> epilogue -> TMA store */
+  EDET_PW_SIMT = 1     /* plain CUDA-core kernel, kept only as an on-device cross-check */
+};
+
+int edet_version(void);
+const char* edet_last_error(void);
+/* Number of SMs / compute capability of the current device (major*10+minor). */
+int edet_device_info(int* sm_count, int* cc);
+
+/*
+ * Stem: Conv2D 3x3 stride 2 'same' (3 -> cout, no bias) + BN + act.
+ * Replaces backbone/efficientnet_model.py:511-527 (Stem.call).
+ *   in   float32 [n, h, w, 3] NHWC            out  half [n, ceil(h/2), ceil(w/2), cout]
+ *   w    half [27][cout]  (ky, kx, cin major; BN scale folded)      bias float32 [cout]
+ */
+int edet_stem_conv(const float* in, edet_half* out, const edet_half* w, const float* bias,
+                   int n, int h, int wd, int cout, int act, edet_stream_t stream);
+
+/*
+ * Pointwise (1x1) convolution as a GEMM with fused epilogue:
+ *   out[b, r, :] = act( A[b, r, :] @ Wt[b or 0]^T + bias ) (+ residual[b, r, :])
+ * Replaces Conv2D 1x1 + BN (+ swish) (+ residual add):
+ *   expand  backbone/efficientnet_model.py:303-317, 388
+ *   project backbone/efficientnet_model.py:345-358, 399-412 (SE excitation enters through the
+ *           per-image pre-scaled weights written by edet_se_fc, so A is read once, unscaled)
+ *   resample 1x1  efficientdet_arch.py:78-95
+ *   separable-conv pointwise halves  efficientdet_arch.py:512-533, 149-191, 206-249
+ *   a     half [batch, rows, k]   (pixel stride lda)
+ *   wt    half [wbatch, nout, k]  (k contiguous; wbatch is 1 or batch)
+ *   out   half [batch, rows, nout] (pixel stride ldo >= nout)
+ *   residual  nullable, same shape/stride convention as out (ldr)
+ * k, lda, ldo, ldr multiples of 8.  impl: EDET_PW_*.
+ */
+int edet_pointwise_conv(const edet_half* a, int lda, const edet_half* wt, int wbatch,
+                        const float* bias, const edet_half* residual, int ldr, edet_half* out,
+                        int ldo, int batch, int rows, int k, int nout, int act, int impl,
+                        edet_stream_t stream);
+
+/*
+ * Depthwise k x k convolution 'same' (k in {3,5}, stride in {1,2}) + bias + act, optionally
+ * emitting per-(image, tile, channel) partial sums of the activated output for the SE squeeze.
+ * Replaces DepthwiseConv2D + BN + swish  backbone/efficientnet_model.py:320-333, 391 and the
+ * depthwise half of SeparableConv2D  efficientdet_arch.py:149-191, 206-249 (bias NULL, act NONE).
+ *   in   half [n, h, w, c]     out  half [n, ceil(h/s), ceil(w/s), c]
+ *   w    half [k*k][c] (BN scale folded)        bias float32 [c] or NULL
+ *   se_partial  float32 [n, edet_depthwise_tiles(...), c] or NULL
+ */
+int edet_depthwise_tiles(int h, int wd, int c, int k, int stride);
+int edet_depthwise_conv(const edet_half* in, edet_half* out, const edet_half* w,
+                        const float* bias, float* se_partial, int n, int h, int wd, int c, int k,
+                        int stride, int act, edet_stream_t stream);
+
+/*
+ * Squeeze-and-excitation gate, and the excitation folded into the project weights:
+ *   mean = sum(partials) * inv_hw ; s = sigmoid(W2 @ act(W1 @ mean + b1) + b2)
+ *   wt_scaled[img, o, c] = wt[o, c] * s[img, c]
+ * Replaces backbone/efficientnet_model.py:183-195 (SE.call) and the multiply at :195.
+ *   partial  float32 [n, tiles, c]      w1 float32 [se][c], b1 [se], w2 float32 [c][se], b2 [c]
+ *   gate     float32 [n, c] (output, always written)
+ *   wt       half [nout][c] project weights (nullable -> only the gate is produced)
+ *   wt_scaled half [n][nout][c]
+ */
+int edet_se_fc(const float* partial, int tiles, float inv_hw, const float* w1, const float* b1,
+               const float* w2, const float* b2, float* gate, const edet_half* wt,
+               edet_half* wt_scaled, int n, int c, int se, int nout, int act,
+               edet_stream_t stream);
+
+/*
+ * One BiFPN node in a single pass: per input {identity | TF1 nearest-neighbour upsample |
+ * max-pool (pool, stride, 'SAME') downsample} -> weighted fusion -> act -> depthwise 3x3 'same'.
+ * Replaces resample_feature_map efficientdet_arch.py:100-130, fuse_features :418-475 (the
+ * normalised weights are computed on the host from WSM; 'sum' passes 1.0), activation :509-510
+ * and the depthwise half of the SeparableConv2D :512-525.
+ */
+enum { EDET_RS_SAME = 0, EDET_RS_UP = 1, EDET_RS_DOWN = 2 };
+typedef struct {
+  const edet_half* ptr; /* half [n, h, w, c] */
+  int h, w;
+  int mode;             /* EDET_RS_* */
+  int pool_h, pool_w, stride_h, stride_w; /* EDET_RS_DOWN only */
+  float weight;         /* normalised fusion weight of this input */
+} edet_fuse_input;
+int edet_fuse_dw(const edet_fuse_input* h_inputs, int n_inputs, const edet_half* dw_w,
+                 edet_half* out, int n, int h, int wd, int c, int act, edet_stream_t stream);
+
+/* Max-pool 'SAME' (padded cells never win). Replaces efficientdet_arch.py:103-112 for the
+ * P6/P7/P8 extra levels (efficientdet_arch.py:369-387). */
+int edet_max_pool(const edet_half* in, edet_half* out, int n, int h, int wd, int c, int pool_h,
+                  int pool_w, int stride_h, int stride_w, edet_stream_t stream);
+
+/*
+ * Pre-NMS: per image and anchor, max / argmax over classes, sigmoid, anchor box decode.
+ * Replaces tf2/postprocess.py:67-156 (merge_class_box_level_outputs, topk_class_boxes with
+ * max_nms_inputs == 0, pre_nms) and tf2/anchors.py:30-58 (decode_box_outputs).
+ *   h_cls[l] half [n, h_l, w_l, ld_cls] (anchor-major, class-minor: a*num_classes + c)
+ *   h_box[l] half [n, h_l, w_l, ld_box] (a*4 + {ty,tx,th,tw})
+ *   anchors  float32 [total_anchors, 4]
+ *   boxes float32 [n, total, 4]  scores float32 [n, total]  classes int32 [n, total]
+ */
+int edet_pre_nms(const edet_half* const* h_cls, const edet_half* const* h_box,
+                 const int* h_level_hw /* [levels][2] */, int levels, int ld_cls, int ld_box,
+                 int num_anchors, int num_classes, const float* anchors, float* boxes,
+                 float* scores, int32_t* classes, int n, edet_stream_t stream);
+
+/*
+ * Global NMS with tf.raw_ops.NonMaxSuppressionV5 semantics (hard, or gaussian soft when
+ * soft_nms_sigma > 0), padded to max_output_size, then gather + class offset + clip + scale
+ * into the serving layout.  Replaces tf2/postprocess.py:159-205 (nms), :375-406
+ * (postprocess_global), :61-64 (clip_boxes) and inference.py:233-271 (det_post_process).
+ *   detections float32 [n, max_output_size, 7] rows [image_id, ymin, xmin, ymax, xmax, score, class]
+ *              (image_id = image_id_base + index in this call: the rank's offset in a sharded batch)
+ *   sel_index int32 [n, max_output_size] (selected anchor index, 0 padded), valid int32 [n]
+ *   work  scratch, edet_nms_work_bytes(n, k) bytes
+ */
+size_t edet_nms_work_bytes(int n, int k);
+int edet_nms_v5(const float* boxes, const float* scores, const int32_t* classes,
+                const float* image_scales /* [n] or NULL */, int image_id_base, int n, int k,
+                int max_output_size,
+                float iou_threshold, float score_threshold, float soft_nms_sigma,
+                float clip_h, float clip_w, float* detections, int32_t* sel_index,
+                int32_t* valid, void* work, edet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUTOML_B200_H_ */

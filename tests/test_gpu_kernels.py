@@ -1,0 +1,315 @@
+"""GPU parity tests: every CUDA entry point (called through the C-ABI) against the CPU oracle on
+the same seeded inputs.  Integer / index outputs must match exactly; floating point within the
+tolerance written next to each assert (fp16 storage, fp32 accumulation)."""
+import numpy as np
+import pytest
+import torch
+
+from automl_b200 import anchors as anchors_lib
+from automl_b200 import utils
+from oracle import efficientdet_oracle as eo
+from oracle import postprocess_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+
+
+def _ops():
+  from automl_b200 import ops  # deferred: loads the CUDA library
+  return ops
+
+
+def rel_l2(a, b):
+  a, b = a.double().flatten(), b.double().flatten()
+  return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+def act_ref(x, act):
+  return {utils.ACT_NONE: lambda t: t, utils.ACT_SWISH: lambda t: t * torch.sigmoid(t),
+          utils.ACT_RELU6: lambda t: torch.clamp(t, 0, 6)}[act](x)
+
+
+# ---------------------------------------------------------------------------------------------
+PW_CASES = [
+    # batch, rows, k, nout, act, residual, per-image weights
+    (1, 128, 64, 64, utils.ACT_NONE, False, False),
+    (1, 1000, 16, 96, utils.ACT_SWISH, False, False),       # K < 64 (TMA zero fill), ragged M
+    (1, 777, 24, 144, utils.ACT_SWISH, False, False),       # K not a multiple of 16
+    (1, 4096, 144, 24, utils.ACT_NONE, True, False),        # project + skip
+    (2, 400, 1152, 192, utils.ACT_NONE, True, True),        # SE-scaled weights, rows % 128 != 0
+    (3, 100, 672, 112, utils.ACT_NONE, False, True),
+    (1, 2048, 192, 1152, utils.ACT_SWISH, False, False),    # nout > 256 -> several N tiles
+    (1, 640, 64, 810, utils.ACT_NONE, False, False),        # class-predict, nout % 8 != 0
+    (1, 25, 64, 36, utils.ACT_NONE, False, False),          # box-predict on a 5x5 level
+    (2, 6400, 40, 64, utils.ACT_NONE, False, False),
+    (1, 50000, 32, 16, utils.ACT_NONE, False, False),       # many tiles per CTA (pipeline wrap)
+    (1, 3000, 320, 64, utils.ACT_RELU6, False, False),
+]
+
+
+@pytest.mark.parametrize('impl_name', ['tcgen05', 'simt'])
+@pytest.mark.parametrize('case', PW_CASES)
+def test_pointwise_conv(case, impl_name):
+  ops = _ops()
+  impl = ops.PW_TCGEN05 if impl_name == 'tcgen05' else ops.PW_SIMT
+  batch, rows, k, nout, act, has_res, per_image = case
+  g = torch.Generator().manual_seed(1234 + rows + k + nout)
+  a = torch.randn(batch, rows, k, generator=g).half()
+  wb = batch if per_image else 1
+  w = (torch.randn(wb, nout, k, generator=g) / np.sqrt(k)).half()
+  bias = torch.randn(nout, generator=g)
+  ldo = (nout + 7) // 8 * 8
+  res = torch.randn(batch, rows, ldo, generator=g).half() if has_res else None
+  out = torch.full((batch, rows, ldo), 7.0).half().to(DEV)
+  ops.pointwise_conv(a.to(DEV), w.to(DEV), bias.to(DEV), out, act,
+                     residual=res.to(DEV) if has_res else None, rows=rows, batch=batch, nout=nout,
+                     impl=impl)
+  torch.cuda.synchronize()
+  ref = torch.einsum('brk,bnk->brn', a.double(), w.double().expand(batch, nout, k)) + bias.double()
+  ref = act_ref(ref, act)
+  if has_res:
+    ref = ref + res[..., :nout].double()
+  got = out.cpu()[..., :nout].double()
+  # fp16 output rounding (2^-11 relative) + fp32 accumulation
+  assert torch.allclose(got, ref, rtol=2e-3, atol=2e-3), float((got - ref).abs().max())
+  assert rel_l2(got, ref) < 5e-4
+  if ldo > nout:  # padding columns must be left untouched
+    assert bool((out.cpu()[..., nout:] == 7.0).all())
+
+
+# ---------------------------------------------------------------------------------------------
+DW_CASES = [
+    # n, h, w, c, k, s, act, bias, se
+    (2, 40, 40, 96, 3, 1, utils.ACT_SWISH, True, True),
+    (1, 33, 47, 32, 3, 2, utils.ACT_SWISH, True, True),     # odd sizes, asymmetric SAME pad
+    (2, 20, 20, 240, 5, 1, utils.ACT_SWISH, True, True),
+    (1, 31, 29, 144, 5, 2, utils.ACT_SWISH, True, True),
+    (2, 10, 10, 64, 3, 1, utils.ACT_NONE, False, False),    # head / BiFPN depthwise half
+    (1, 5, 5, 64, 3, 1, utils.ACT_NONE, False, False),
+    (1, 64, 64, 1152, 5, 1, utils.ACT_SWISH, True, True),
+    (1, 12, 12, 672, 5, 2, utils.ACT_RELU6, True, False),
+]
+
+
+@pytest.mark.parametrize('case', DW_CASES)
+def test_depthwise_conv(case):
+  ops = _ops()
+  n, h, w, c, k, s, act, has_bias, has_se = case
+  g = torch.Generator().manual_seed(99 + h + c + k)
+  x = torch.randn(n, h, w, c, generator=g).half()
+  wk = (torch.randn(k, k, c, generator=g) / k).half()
+  bias = torch.randn(c, generator=g) * 0.1 if has_bias else None
+  ho, wo = -(-h // s), -(-w // s)
+  out = torch.empty(n, ho, wo, c, dtype=torch.float16, device=DEV)
+  partial = None
+  if has_se:
+    tiles = ops.depthwise_tiles(h, w, c, k, s)
+    partial = torch.full((n, tiles, c), float('nan'), device=DEV)
+  ops.depthwise_conv(x.to(DEV), out, wk.reshape(k * k, c).to(DEV),
+                     bias.to(DEV) if has_bias else None, act, k, s, partial)
+  torch.cuda.synchronize()
+  ref = eo.depthwise_conv2d_same(x.double().permute(0, 3, 1, 2), wk.double().unsqueeze(-1), s)
+  if has_bias:
+    ref = ref + bias.double().view(1, -1, 1, 1)
+  ref = act_ref(ref, act).permute(0, 2, 3, 1)
+  got = out.cpu().double()
+  assert got.shape == ref.shape
+  assert torch.allclose(got, ref, rtol=2e-3, atol=2e-3), float((got - ref).abs().max())
+  if has_se:
+    sums = partial.cpu().double().sum(1)
+    np.testing.assert_allclose(sums.numpy(), ref.sum((1, 2)).numpy(), rtol=1e-4, atol=1e-3)
+
+
+def test_se_fc():
+  ops = _ops()
+  n, tiles, c, se, nout = 3, 7, 96, 4, 24
+  g = torch.Generator().manual_seed(5)
+  partial = torch.randn(n, tiles, c, generator=g)
+  w1, b1 = torch.randn(se, c, generator=g) * 0.2, torch.randn(se, generator=g) * 0.1
+  w2, b2 = torch.randn(c, se, generator=g) * 0.5, torch.randn(c, generator=g) * 0.1
+  wt = torch.randn(nout, c, generator=g).half()
+  gate = torch.empty(n, c, device=DEV)
+  wt_scaled = torch.empty(n, nout, c, dtype=torch.float16, device=DEV)
+  inv_hw = 1.0 / 50.0
+  ops.se_fc(partial.to(DEV), inv_hw, w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), gate,
+            utils.ACT_SWISH, wt.to(DEV), wt_scaled)
+  torch.cuda.synchronize()
+  mean = partial.double().sum(1) * inv_hw
+  r = mean @ w1.double().T + b1.double()
+  r = r * torch.sigmoid(r)
+  ref_gate = torch.sigmoid(r @ w2.double().T + b2.double())
+  np.testing.assert_allclose(gate.cpu().double().numpy(), ref_gate.numpy(), rtol=1e-5, atol=1e-6)
+  ref_w = wt.double()[None] * ref_gate[:, None, :]
+  assert torch.allclose(wt_scaled.cpu().double(), ref_w, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize('hw,cout', [((64, 64), 32), ((33, 47), 48), ((8, 8), 64)])
+def test_stem_conv(hw, cout):
+  ops = _ops()
+  h, w = hw
+  g = torch.Generator().manual_seed(3)
+  x = torch.randn(2, h, w, 3, generator=g)
+  k = (torch.randn(3, 3, 3, cout, generator=g) * 0.3).half()
+  bias = torch.randn(cout, generator=g) * 0.1
+  out = torch.empty(2, -(-h // 2), -(-w // 2), cout, dtype=torch.float16, device=DEV)
+  ops.stem_conv(x.to(DEV), out, k.reshape(27, cout).to(DEV), bias.to(DEV), utils.ACT_SWISH)
+  torch.cuda.synchronize()
+  ref = eo.conv2d_same(x.double().permute(0, 3, 1, 2), k.double(), stride=2) + bias.double().view(1, -1, 1, 1)
+  ref = (ref * torch.sigmoid(ref)).permute(0, 2, 3, 1)
+  assert torch.allclose(out.cpu().double(), ref, rtol=2e-3, atol=2e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_fuse_dw_all_modes():
+  """One node with an identity input, a nearest-upsampled input and a max-pooled input."""
+  ops = _ops()
+  n, c = 2, 88
+  for (h, w) in [(20, 20), (13, 9)]:
+    g = torch.Generator().manual_seed(h * 100 + w)
+    uh, uw = (h - 1) // 2 + 1, (w - 1) // 2 + 1          # coarser level -> upsample
+    dh, dw = h * 2 - (h % 2), w * 2 - (w % 2)            # finer level  -> max-pool 3x3 s2
+    assert -(-dh // 2) == h and -(-dw // 2) == w
+    same = torch.randn(n, h, w, c, generator=g).half()
+    up = torch.randn(n, uh, uw, c, generator=g).half()
+    down = torch.randn(n, dh, dw, c, generator=g).half()
+    wts = [0.5, 0.3, 0.2]
+    dwk = (torch.randn(3, 3, c, generator=g) / 3).half()
+    out = torch.empty(n, h, w, c, dtype=torch.float16, device=DEV)
+    specs = [(same.to(DEV), ops.RS_SAME, None, wts[0]), (up.to(DEV), ops.RS_UP, None, wts[1]),
+             (down.to(DEV), ops.RS_DOWN, (3, 3, 2, 2), wts[2])]
+    ops.fuse_dw(specs, dwk.reshape(9, c).to(DEV), out, utils.ACT_SWISH)
+    torch.cuda.synchronize()
+    nchw = lambda t: t.double().permute(0, 3, 1, 2)
+    fused = (nchw(same) * np.float32(wts[0]) + eo.resize_nearest_tf1(nchw(up), h, w) * np.float32(wts[1]) +
+             eo.max_pool_same(nchw(down), (3, 3), (2, 2)) * np.float32(wts[2]))
+    fused = fused * torch.sigmoid(fused)
+    ref = eo.depthwise_conv2d_same(fused, dwk.double().unsqueeze(-1)).permute(0, 2, 3, 1)
+    assert torch.allclose(out.cpu().double(), ref, rtol=2e-3, atol=2e-3), (h, w)
+
+
+def test_max_pool():
+  ops = _ops()
+  for (h, w) in [(20, 20), (5, 5), (13, 9)]:
+    x = torch.randn(2, h, w, 64, generator=torch.Generator().manual_seed(h)).half()
+    out = torch.empty(2, -(-h // 2), -(-w // 2), 64, dtype=torch.float16, device=DEV)
+    ops.max_pool(x.to(DEV), out, (3, 3), (2, 2))
+    torch.cuda.synchronize()
+    ref = eo.max_pool_same(x.permute(0, 3, 1, 2).float(), (3, 3), (2, 2)).permute(0, 2, 3, 1)
+    assert torch.equal(out.cpu().float(), ref)      # max of fp16 values is exact
+
+
+# ---------------------------------------------------------------------------------------------
+def _synthetic_head_outputs(rng, n, image_size, min_level=3, max_level=7, a=9, c=90):
+  fs = utils.get_feat_sizes(image_size, max_level)
+  cls, box = [], []
+  for l in range(min_level, max_level + 1):
+    h, w = fs[l]['height'], fs[l]['width']
+    cls.append(rng.normal(-4.0, 2.0, size=(n, h, w, a * c)).astype(np.float16))
+    box.append(rng.normal(0.0, 0.5, size=(n, h, w, a * 4)).astype(np.float16))
+  return cls, box
+
+
+def _params(image_size, method='gaussian', **nms_over):
+  nms = {'method': method, 'iou_thresh': None, 'score_thresh': 0., 'sigma': None,
+         'pyfunc': False, 'max_nms_inputs': 0, 'max_output_size': 100}
+  nms.update(nms_over)
+  return {'min_level': 3, 'max_level': 7, 'num_scales': 3, 'aspect_ratios': [1.0, 2.0, 0.5],
+          'anchor_scale': 4.0, 'image_size': image_size, 'num_classes': 90,
+          'data_format': 'channels_last', 'nms_configs': nms}
+
+
+def _pad_ld(arr, ld):
+  out = np.zeros(arr.shape[:-1] + (ld,), arr.dtype)
+  out[..., :arr.shape[-1]] = arr
+  return out
+
+
+@pytest.mark.parametrize('image_size', [128, (96, 160)])
+def test_pre_nms(image_size):
+  ops = _ops()
+  rng = np.random.default_rng(11)
+  n = 2
+  cls, box = _synthetic_head_outputs(rng, n, image_size)
+  params = _params(image_size)
+  ref_boxes, ref_scores, ref_classes = po.pre_nms(params, cls, box)
+  anc = anchors_lib.Anchors(3, 7, 3, [1.0, 2.0, 0.5], 4.0, image_size).boxes
+  k = anc.shape[0]
+  cls_d = [torch.from_numpy(_pad_ld(t, 816)).to(DEV) for t in cls]
+  box_d = [torch.from_numpy(_pad_ld(t, 40)).to(DEV) for t in box]
+  boxes = torch.empty(n, k, 4, device=DEV)
+  scores = torch.empty(n, k, device=DEV)
+  classes = torch.empty(n, k, dtype=torch.int32, device=DEV)
+  hw = [(t.shape[1], t.shape[2]) for t in cls]
+  ops.pre_nms(cls_d, box_d, hw, 9, 90, torch.from_numpy(anc).to(DEV), boxes, scores, classes)
+  torch.cuda.synchronize()
+  np.testing.assert_array_equal(classes.cpu().numpy(), ref_classes)          # bit-exact indices
+  np.testing.assert_allclose(scores.cpu().numpy(), ref_scores, rtol=1e-6, atol=1e-7)
+  np.testing.assert_allclose(boxes.cpu().numpy(), ref_boxes, rtol=1e-5, atol=1e-4)
+
+
+def _nms_inputs(rng, n, k, image=512.0, clustered=True):
+  if clustered:
+    centres = rng.uniform(0, image, size=(n, 40, 2))
+    pick = rng.integers(0, 40, size=(n, k))
+    c = np.take_along_axis(centres, pick[..., None].repeat(2, -1), 1) + rng.normal(0, 8, size=(n, k, 2))
+  else:
+    c = rng.uniform(0, image, size=(n, k, 2))
+  wh = np.exp(rng.uniform(np.log(8), np.log(image / 2), size=(n, k, 2)))
+  boxes = np.concatenate([c - wh / 2, c + wh / 2], -1).astype(np.float32)   # [ymin,xmin,ymax,xmax]
+  scores = (1 / (1 + np.exp(-rng.normal(-3, 2, size=(n, k))))).astype(np.float32)
+  classes = rng.integers(0, 90, size=(n, k)).astype(np.int32)
+  return boxes, scores, classes
+
+
+@pytest.mark.parametrize('method,k', [('gaussian', 3000), ('hard', 3000), ('gaussian', 20000),
+                                      ('hard', 49104), ('gaussian', 64)])
+def test_nms_v5_bit_exact(method, k):
+  ops = _ops()
+  rng = np.random.default_rng(k + len(method))
+  n = 3
+  boxes, scores, classes = _nms_inputs(rng, n, k)
+  if method == 'hard':   # exercise exact ties: duplicate scores and boxes
+    scores[:, 1::7] = scores[:, 0:1]
+    boxes[:, 5] = boxes[:, 4]
+  params = _params(512, method=method, score_thresh=0.0 if method == 'gaussian' else None)
+  iou_t, score_t, tf_sigma = po.nms_v5_params(params['nms_configs'])
+  scales = np.asarray([1.0, 1.5, 0.75], np.float32)
+  det = torch.empty(n, 100, 7, device=DEV)
+  sel = torch.empty(n, 100, dtype=torch.int32, device=DEV)
+  valid = torch.empty(n, dtype=torch.int32, device=DEV)
+  work = torch.empty(ops.nms_work_bytes(n, k), dtype=torch.uint8, device=DEV)
+  ops.nms_v5(torch.from_numpy(boxes).to(DEV), torch.from_numpy(scores).to(DEV),
+             torch.from_numpy(classes).to(DEV), torch.from_numpy(scales).to(DEV), 0, 100, iou_t,
+             score_t, tf_sigma, (512.0, 512.0), det, sel, valid, work)
+  torch.cuda.synchronize()
+  det, sel, valid = det.cpu().numpy(), sel.cpu().numpy(), valid.cpu().numpy()
+  for i in range(n):
+    idx, sc, v = po.non_max_suppression_v5(boxes[i], scores[i], 100, iou_t, score_t, tf_sigma, True)
+    assert valid[i] == v
+    np.testing.assert_array_equal(sel[i], idx)                      # bit-exact keep indices
+    np.testing.assert_array_equal(det[i, :, 5], sc)                 # bit-exact (soft) scores
+    ref_boxes = po.clip_boxes(boxes[i][idx], 512) * scales[i]
+    np.testing.assert_array_equal(det[i, :, 1:5], ref_boxes)
+    np.testing.assert_array_equal(det[i, :, 6], (classes[i][idx] + 1).astype(np.float32))
+    np.testing.assert_array_equal(det[i, :, 0], np.full(100, i, np.float32))
+
+
+def test_nms_v5_fewer_than_max_and_empty():
+  ops = _ops()
+  rng = np.random.default_rng(0)
+  boxes, scores, classes = _nms_inputs(rng, 2, 50)
+  scores[1] = 0.0005          # nothing passes score_thresh 0.001 in image 1
+  det = torch.empty(2, 100, 7, device=DEV)
+  sel = torch.empty(2, 100, dtype=torch.int32, device=DEV)
+  valid = torch.empty(2, dtype=torch.int32, device=DEV)
+  work = torch.empty(ops.nms_work_bytes(2, 50), dtype=torch.uint8, device=DEV)
+  ops.nms_v5(torch.from_numpy(boxes).to(DEV), torch.from_numpy(scores).to(DEV),
+             torch.from_numpy(classes).to(DEV), None, 0, 100, 0.5, 0.001, 0.25, (512.0, 512.0),
+             det, sel, valid, work)
+  torch.cuda.synchronize()
+  idx, sc, v = po.non_max_suppression_v5(boxes[0], scores[0], 100, 0.5, 0.001, 0.25, True)
+  assert int(valid[0]) == v and int(valid[1]) == 0
+  np.testing.assert_array_equal(sel[0].cpu().numpy(), idx)
+  np.testing.assert_array_equal(det[0, :, 5].cpu().numpy(), sc)
+  assert float(det[1, :, 5].abs().max()) == 0.0

@@ -1,0 +1,124 @@
+"""End-to-end parity of the CUDA network against the CPU oracle on identical seeded weights and
+inputs (the reference's own TF path cannot run offline; see oracle/efficientdet_oracle.py).
+
+Tolerance (north_star: "within 1e-3 relative"): per-tensor relative L2 error <= 1e-3 on every
+level's feature map and on the class / box outputs, plus a max-abs bound; activations are
+stored in fp16 (2^-11 relative per tensor), accumulated in fp32."""
+import numpy as np
+import pytest
+import torch
+
+from automl_b200 import arch
+from automl_b200 import hparams_config
+from automl_b200 import weights
+from oracle import efficientdet_oracle as eo
+from oracle import postprocess_oracle as po
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-3
+
+
+def rel_l2(a, b):
+  a, b = a.double().flatten(), b.double().flatten()
+  return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+def _setup(name, image_size, n, seed=0, **over):
+  c = hparams_config.get_efficientdet_config(name)
+  c.override(dict(image_size=image_size, **over))
+  a = arch.DetArch(c)
+  w = weights.synthetic_weights(a, seed)
+  h, wd = a.image_hw
+  x = np.random.default_rng(seed + 1).uniform(-2.0, 2.0, size=(n, h, wd, 3)).astype(np.float32)
+  return c, a, w, x
+
+
+def _engine(c, w, n, **kw):
+  from automl_b200.engine import Engine
+  return Engine(c, w, n, **kw)
+
+
+@pytest.mark.parametrize('impl', ['tcgen05', 'simt'])
+@pytest.mark.parametrize('name,image_size,n', [
+    ('efficientdet-d0', 128, 2),
+    ('efficientdet-d0', (96, 160), 1),     # non-square
+    ('efficientdet-d0', (127, 129), 1),    # odd sizes (efficientdet_arch_test.py:52-58)
+])
+def test_network_parity(name, image_size, n, impl):
+  from automl_b200 import ops
+  c, a, w, x = _setup(name, image_size, n)
+  orc = eo.Oracle(c, w, torch.float32)
+  cls_ref, box_ref = orc(x)
+  eng = _engine(c, w, n, pw_impl=ops.PW_TCGEN05 if impl == 'tcgen05' else ops.PW_SIMT,
+                use_cuda_graph=False)
+  cls_out, box_out = eng.forward(torch.from_numpy(x))
+  torch.cuda.synchronize()
+  # intermediate feature maps: backbone endpoints and BiFPN outputs
+  for b in a.blocks:
+    got = eng.buffers[b.name + '/out'].float().cpu().permute(0, 3, 1, 2)
+    assert rel_l2(got, orc.endpoints[b.name]) < REL_TOL, b.name
+  for l in a.levels:
+    got = eng.fpn_feats[l].float().cpu().permute(0, 3, 1, 2)
+    assert rel_l2(got, orc.endpoints['fpn_%d' % l]) < REL_TOL, 'fpn %d' % l
+  for l in a.levels:
+    gc, gb = cls_out[l].float().cpu(), box_out[l].float().cpu()
+    assert gc.shape == cls_ref[l].shape and gb.shape == box_ref[l].shape
+    assert rel_l2(gc, cls_ref[l]) < REL_TOL, 'cls %d' % l
+    assert rel_l2(gb, box_ref[l]) < REL_TOL, 'box %d' % l
+    assert float((gc - cls_ref[l]).abs().max()) < 2e-2
+    assert float((gb - box_ref[l]).abs().max()) < 5e-3
+
+
+def test_network_parity_d1_relu6_sum():
+  """A second backbone (b1), a non-swish activation and 'sum' fusion (the D6/D7 setting)."""
+  c, a, w, x = _setup('efficientdet-d1', 128, 1, seed=3, act_type='relu6', fpn_weight_method='sum')
+  cls_ref, box_ref = eo.Oracle(c, w, torch.float32)(x)
+  eng = _engine(c, w, 1, use_cuda_graph=False)
+  cls_out, box_out = eng.forward(torch.from_numpy(x))
+  torch.cuda.synchronize()
+  for l in a.levels:
+    assert rel_l2(cls_out[l].float().cpu(), cls_ref[l]) < REL_TOL
+    assert rel_l2(box_out[l].float().cpu(), box_ref[l]) < REL_TOL
+
+
+def test_detect_matches_oracle_postprocess_and_graph_replay():
+  c, a, w, x = _setup('efficientdet-d0', 128, 2, seed=5)
+  eng = _engine(c, w, 2, use_cuda_graph=True, image_id_base=4)
+  scales = np.asarray([1.25, 0.5], np.float32)
+  det1 = eng.detect(torch.from_numpy(x), scales).cpu().numpy().copy()
+  det2 = eng.detect(torch.from_numpy(x), scales).cpu().numpy().copy()   # graph replay
+  np.testing.assert_array_equal(det1, det2)                             # deterministic
+  assert det1.shape == (2, 100, 7)
+  np.testing.assert_array_equal(det1[:, :, 0], np.asarray([[4.0] * 100, [5.0] * 100], np.float32))
+
+  params = c.as_dict()
+  cls_l = [eng.cls_out[l][..., :810].float().cpu().numpy() for l in a.levels]
+  box_l = [eng.box_out[l][..., :36].float().cpu().numpy() for l in a.levels]
+  ref_boxes, ref_scores, ref_classes = po.pre_nms(params, cls_l, box_l)
+  np.testing.assert_array_equal(eng.classes.cpu().numpy(), ref_classes)
+  np.testing.assert_allclose(eng.scores.cpu().numpy(), ref_scores, rtol=1e-6, atol=1e-7)
+  np.testing.assert_allclose(eng.boxes.cpu().numpy(), ref_boxes, rtol=1e-5, atol=1e-4)
+  # NMS: the oracle on the device's own pre-NMS tensors must give bit-identical detections
+  gb, gs, gc = eng.boxes.cpu().numpy(), eng.scores.cpu().numpy(), eng.classes.cpu().numpy()
+  iou_t, score_t, tf_sigma = po.nms_v5_params(params['nms_configs'])
+  for i in range(2):
+    idx, sc, v = po.non_max_suppression_v5(gb[i], gs[i], 100, iou_t, score_t, tf_sigma, True)
+    assert int(eng.valid[i]) == v
+    np.testing.assert_array_equal(eng.sel_index[i].cpu().numpy(), idx)
+    np.testing.assert_array_equal(det1[i, :, 5], sc)
+    np.testing.assert_array_equal(det1[i, :, 1:5], po.clip_boxes(gb[i][idx], 128) * scales[i])
+    np.testing.assert_array_equal(det1[i, :, 6], (gc[i][idx] + 1).astype(np.float32))
+
+
+def test_efficientdet_call_surface():
+  from automl_b200 import efficientdet_arch
+  with pytest.raises(ValueError):
+    efficientdet_arch.efficientdet(torch.zeros(1, 64, 64, 3))
+  with pytest.raises(KeyError):
+    efficientdet_arch.efficientdet(torch.zeros(1, 64, 64, 3), model_name='efficientdet-d0',
+                                   not_a_key=1)
+  x = torch.zeros(1, 64, 64, 3)
+  cls_out, box_out = efficientdet_arch.efficientdet(x, model_name='efficientdet-d0', image_size=64)
+  assert sorted(cls_out) == [3, 4, 5, 6, 7]
+  assert tuple(cls_out[3].shape) == (1, 8, 8, 810) and tuple(box_out[7].shape) == (1, 1, 1, 36)
+  assert cls_out[3].dtype == torch.float32
