@@ -17,8 +17,8 @@ constexpr int kDwThreads = 256;
 
 template <int K, int S>
 struct DwCfg {
-  // 5x5: 4 channels per thread (64-bit accesses) to keep the 25-tap weight set in registers
-  // without spilling; 3x3: 8 channels per thread (128-bit accesses).
+  // 5x5: 4 channels per thread (64-bit accesses) so the 25-tap fp32 weight set fits in
+  // registers; 3x3: 8 channels per thread (128-bit accesses).
   static constexpr int CPT = (K == 5) ? 4 : 8;
   static constexpr int ROWS = (S == 2) ? 4 : 8;             // output rows per thread
   static constexpr int IN_ROWS = (ROWS - 1) * S + K;        // input rows touched
@@ -28,15 +28,14 @@ template <int CPT> struct VecT;
 template <> struct VecT<8> { using type = uint4; };
 template <> struct VecT<4> { using type = uint2; };
 
+// The arithmetic runs on channel PAIRS with the packed fp32 FMA of sm_100 (FFMA2): a 5x5
+// depthwise conv needs 25 MACs per output element, which at the HBM rate is more than the
+// scalar FFMA pipe can issue, so the packed form is what keeps this kernel memory-bound.
 template <int CPT>
-__device__ __forceinline__ void vec_to_float(const typename VecT<CPT>::type& v, float* f) {
+__device__ __forceinline__ void vec_to_float2(const typename VecT<CPT>::type& v, float2* f) {
   const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-  for (int i = 0; i < CPT / 2; ++i) {
-    const float2 t = __half22float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+  for (int i = 0; i < CPT / 2; ++i) f[i] = __half22float2(h[i]);
 }
 template <int CPT>
 __device__ __forceinline__ typename VecT<CPT>::type float_to_vec(const float* f) {
@@ -54,6 +53,7 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
                  float* __restrict__ se_partial, int h, int wd, int c, int ho, int wo, int pad_t,
                  int pad_l) {
   constexpr int CPT = DwCfg<K, S>::CPT;
+  constexpr int P = CPT / 2;  // channel pairs
   constexpr int ROWS = DwCfg<K, S>::ROWS;
   constexpr int IN_ROWS = DwCfg<K, S>::IN_ROWS;
   using Vec = typename VecT<CPT>::type;
@@ -71,17 +71,19 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
   for (int i = 0; i < CPT; ++i) ssum[i] = 0.f;
 
   if (active) {
-    // folded weights for this channel group: [K*K] x CPT halves, kept packed in registers
-    Vec wreg[K * K];
+    // folded weights for this channel group, converted once to fp32 pairs
+    float2 wreg[K * K][P];
 #pragma unroll
-    for (int t = 0; t < K * K; ++t)
-      wreg[t] = __ldg(reinterpret_cast<const Vec*>(w + static_cast<size_t>(t) * c + ch));
+    for (int t = 0; t < K * K; ++t) {
+      const Vec wv = __ldg(reinterpret_cast<const Vec*>(w + static_cast<size_t>(t) * c + ch));
+      vec_to_float2<CPT>(wv, wreg[t]);
+    }
 
-    float acc[ROWS][CPT];
+    float2 acc[ROWS][P];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) acc[r][i] = 0.f;
+      for (int i = 0; i < P; ++i) acc[r][i] = make_float2(0.f, 0.f);
 
     const __half* in_n = in + static_cast<size_t>(n) * h * wd * c;
     const int iy0 = oy0 * S - pad_t;
@@ -91,7 +93,7 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
     for (int ir = 0; ir < IN_ROWS; ++ir) {
       const int iy = iy0 + ir;
       const bool row_ok = (iy >= 0) && (iy < h);
-      float xv[K][CPT];
+      float2 xv[K][P];
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
         const int ix = ix0 + kx;
@@ -99,7 +101,7 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
         memset(&v, 0, sizeof(v));
         if (row_ok && ix >= 0 && ix < wd)
           v = __ldg(reinterpret_cast<const Vec*>(in_n + (static_cast<size_t>(iy) * wd + ix) * c + ch));
-        vec_to_float<CPT>(v, xv[kx]);
+        vec_to_float2<CPT>(v, xv[kx]);
       }
       // input row ir feeds output row r through tap ky = ir - r*S
 #pragma unroll
@@ -107,12 +109,10 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
         const int ky = ir - r * S;
         if (ky >= 0 && ky < K) {
 #pragma unroll
-          for (int kx = 0; kx < K; ++kx) {
-            float wf[CPT];
-            vec_to_float<CPT>(wreg[ky * K + kx], wf);
+          for (int kx = 0; kx < K; ++kx)
 #pragma unroll
-            for (int i = 0; i < CPT; ++i) acc[r][i] = fmaf(xv[kx][i], wf[i], acc[r][i]);
-          }
+            for (int i = 0; i < P; ++i)
+              acc[r][i] = __ffma2_rn(xv[kx][i], wreg[ky * K + kx][i], acc[r][i]);
         }
       }
     }
@@ -127,9 +127,13 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
       if (oy < ho) {
         float o[CPT];
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-          o[i] = apply_act_t<ACT>(acc[r][i] + bv[i]);
-          if (HAS_SE) ssum[i] += o[i];
+        for (int i = 0; i < P; ++i) {
+          o[2 * i] = apply_act_t<ACT>(acc[r][i].x + bv[2 * i]);
+          o[2 * i + 1] = apply_act_t<ACT>(acc[r][i].y + bv[2 * i + 1]);
+        }
+        if (HAS_SE) {
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) ssum[i] += o[i];
         }
         *reinterpret_cast<Vec*>(out_n + (static_cast<size_t>(oy) * wo + ox) * c + ch) =
             float_to_vec<CPT>(o);
@@ -174,12 +178,50 @@ se_fc_kernel(const float* __restrict__ partial, int tiles, float inv_hw,
   float* mean = sm;        // [c]
   float* red = sm + c;     // [se]
   float* g = red + se;     // [c]
+  float* red_scratch = g + c;  // [8][c] worst case is bounded by blockDim.x floats
   const int n = blockIdx.x;
   const float* pn = partial + static_cast<size_t>(n) * tiles * c;
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    float s = 0.f;
-    for (int t = 0; t < tiles; ++t) s += pn[static_cast<size_t>(t) * c + ch];
-    mean[ch] = s * inv_hw;
+  // Squeeze: G thread groups split the tile range of every channel; loads are issued 8 at a
+  // time (this loop is pure latency), partial sums are combined in a fixed order.
+  {
+    const int groups = max(1, min(static_cast<int>(blockDim.x) / c, 8));
+    const int gi = threadIdx.x / c, ch = threadIdx.x % c;
+    float* gsum = g;  // reuse the gate buffer as [groups][c] scratch when it fits
+    if (groups > 1 && gi < groups) {
+      float s = 0.f;
+      for (int t0 = gi; t0 < tiles; t0 += groups * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int t = t0 + u * groups;
+          v[u] = t < tiles ? pn[static_cast<size_t>(t) * c + ch] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+      }
+      red_scratch[gi * c + ch] = s;
+    }
+    (void)gsum;
+    if (groups > 1) {
+      __syncthreads();
+      for (int cc = threadIdx.x; cc < c; cc += blockDim.x) {
+        float s = 0.f;
+        for (int q = 0; q < groups; ++q) s += red_scratch[q * c + cc];
+        mean[cc] = s * inv_hw;
+      }
+    } else {
+      for (int cc = threadIdx.x; cc < c; cc += blockDim.x) {
+        float s = 0.f;
+        for (int t0 = 0; t0 < tiles; t0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = (t0 + u) < tiles ? pn[static_cast<size_t>(t0 + u) * c + cc] : 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        mean[cc] = s * inv_hw;
+      }
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -278,7 +320,7 @@ extern "C" int edet_se_fc(const float* partial, int tiles, float inv_hw, const f
   EDET_CHECK_ARG(partial && w1 && b1 && w2 && b2 && gate, "se_fc: null pointer");
   EDET_CHECK_ARG(n > 0 && c > 0 && c % 8 == 0 && se > 0 && tiles > 0, "se_fc: bad shape");
   EDET_CHECK_ARG(!wt || (wt_scaled && nout > 0), "se_fc: wt given without wt_scaled/nout");
-  const size_t smem = static_cast<size_t>(2 * c + se) * sizeof(float);
+  const size_t smem = static_cast<size_t>(2 * c + se + 256) * sizeof(float);
   EDET_CHECK_ARG(smem <= 48 * 1024, "se_fc: c too large");
   int nsplit = 1;
   if (wt) {

@@ -2,7 +2,8 @@
 //
 //   out[b, r, n] = act( sum_k A[b, r, k] * Wt[b|0, n, k] + bias[n] ) (+ residual[b, r, n])
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (persistent CTAs, two per SM so one CTA's epilogue overlaps the other's loads;
+// 192 threads each):
 //   warp 0      : TMA producer  -- cp.async.bulk.tensor (3-D maps, 128B swizzle) for the A tile
 //                 [128 x 64] and the W tile [block_n x 64] into an N-stage smem ring (mbarrier
 //                 complete_tx).  Out-of-bounds rows / K tail are zero-filled by TMA.
@@ -33,7 +34,7 @@ constexpr int kStoreCols = 64;
 constexpr int kATileBytes = BLOCK_M * BLOCK_K * 2;        // 16 KiB
 constexpr int kStoreBytes = BLOCK_M * kStoreCols * 2;     // 16 KiB
 constexpr int kMaxStages = 8;
-constexpr int kSmemLimit = 232448;                        // 227 KiB
+constexpr int kSmemLimit = 113 * 1024;                    // two CTAs per SM share the 227 KiB
 
 struct Params {
   int batch, rows, k, nout;
@@ -165,7 +166,7 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const Params& p) {
 }
 
 template <int ACT, bool HAS_RES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                     const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_o, const Params p) {
@@ -300,9 +301,12 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       }
       mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
       tc_fence_after();
-      const int num_chunks = (p.block_n + kStoreCols - 1) / kStoreCols;
+      // only the columns that exist in the output are worth an epilogue (rounded up to the
+      // 16-column TMEM load granule); the rest of a ragged last N tile is skipped
+      const int n_valid = min(p.block_n, ((p.nout - n0 + 15) >> 4) << 4);
+      const int num_chunks = (n_valid + kStoreCols - 1) / kStoreCols;
       for (int c = 0; c < num_chunks; ++c, ++store_iter) {
-        const int cols = min(kStoreCols, p.block_n - c * kStoreCols);  // multiple of 16
+        const int cols = min(kStoreCols, n_valid - c * kStoreCols);  // multiple of 16
         const int sb = store_iter % kStoreStages;
         uint8_t* stage_buf = smem_store + sb * kStoreBytes;
         if (e_tid == 0) tma_store_wait_read<kStoreStages - 1>();
@@ -326,11 +330,11 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
         for (int jj = 0; jj < 8; ++jj) {
           if (jj * 8 < cols) {
             float o[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c * kStoreCols + jj * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c * kStoreCols + jj * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float x = v[jj * 8 + e] + bias_s[c * kStoreCols + jj * 8 + e];
-              o[e] = (ACT < 0) ? x : apply_act_t<ACT>(x);
-            }
+            for (int e = 0; e < 8; ++e) o[e] = apply_act_t<ACT>(v[jj * 8 + e] + bb[e]);
             if (HAS_RES) {
               const int col = n0 + c * kStoreCols + jj * 8;
               if (row_ok && col < p.nout) {
@@ -411,18 +415,12 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1,
   return EDET_OK;
 }
 
+// N tile: at most 128 columns so that two CTAs (2 x 2 accumulator stages x 128 TMEM columns,
+// <=113 KiB smem each) are resident per SM.  Wider outputs take several N tiles; the A tile of
+// the extra tiles comes from L2, and the epilogue skips the columns past nout.
 static int pick_block_n(int nout) {
-  if (nout <= 256) return ((nout + 15) / 16) * 16;
-  int best = 256, best_cost = 1 << 30;
-  for (int bn = 256; bn >= 64; bn -= 64) {
-    const int tiles = (nout + bn - 1) / bn;
-    const int cost = tiles * bn + 16 * tiles;
-    if (cost < best_cost) {
-      best_cost = cost;
-      best = bn;
-    }
-  }
-  return best;
+  if (nout <= 128) return ((nout + 15) / 16) * 16;
+  return 128;
 }
 
 template <int ACT, bool HAS_RES>
@@ -463,7 +461,7 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
 
   const int stage_bytes = kATileBytes + p.block_n * BLOCK_K * 2;
   const int fixed = kStoreStages * kStoreBytes + 2 * 256 * 4 + (2 * kMaxStages + 4) * 8 + 16;
-  int stages = (kSmemLimit - 1024 - fixed) / stage_bytes;
+  int stages = (kSmemLimit - 1024 - fixed) / stage_bytes;  // 2 (block_n 128) .. 4 (block_n 16)
   if (stages > kMaxStages) stages = kMaxStages;
   EDET_CHECK_ARG(stages >= 2, "pointwise_tc: block_n %d leaves <2 pipeline stages", p.block_n);
   p.num_stages = stages;
@@ -484,7 +482,7 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
     EDET_CHECK_CUDA(cudaGetDevice(&dev));
     EDET_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = p.total_tiles < sm_count ? p.total_tiles : sm_count;
+  const int grid = p.total_tiles < 2 * sm_count ? p.total_tiles : 2 * sm_count;
   const bool has_res = residual != nullptr;
 
 #define EDET_PW_CASE(A)                                                              \

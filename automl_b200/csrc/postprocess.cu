@@ -109,7 +109,10 @@ nms_v5_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
               int image_id_base, int k, int max_out, float iou_thr, float score_thr, float sigma,
               float clip_h, float clip_w, float* __restrict__ detections,
               int32_t* __restrict__ sel_index, int32_t* __restrict__ valid,
-              float* __restrict__ work_scores, int32_t* __restrict__ work_begin) {
+              float* __restrict__ work_scores, int32_t* __restrict__ work_begin,
+              const int32_t* __restrict__ need_full) {
+  // Full-queue path: only runs for images the shared-memory fast path could not prove exact.
+  if (need_full != nullptr && need_full[blockIdx.x] == 0) return;
   __shared__ float4 sel_box[kNmsMaxOut];
   __shared__ int sel_idx[kNmsMaxOut];
   __shared__ float sel_score[kNmsMaxOut];
@@ -117,7 +120,6 @@ nms_v5_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
   __shared__ float wgt_s[kNmsMaxOut];
   __shared__ float red_s[32];
   __shared__ int red_i[32];
-  __shared__ float best_s;
   __shared__ int best_i;
   __shared__ int nsel_s;
 
@@ -216,7 +218,6 @@ nms_v5_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
           }
           ws[i] = new_s;
           best_i = i;
-          best_s = new_s;
         }
       }
     }
@@ -227,11 +228,20 @@ nms_v5_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
       // owner refreshes its cached local best
       my_s = -CUDART_INF_F;
       my_i = 0x7fffffff;
-      for (int j = tid; j < k; j += kNmsThreads) {
-        const float v = ws[j];
-        if (better(v, j, my_s, my_i)) {
-          my_s = v;
-          my_i = j;
+      for (int j0 = tid; j0 < k; j0 += 8 * kNmsThreads) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {   // issue the loads together: this is latency bound
+          const int j = j0 + u * kNmsThreads;
+          v[u] = j < k ? ws[j] : -CUDART_INF_F;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + u * kNmsThreads;
+          if (j < k && better(v[u], j, my_s, my_i)) {
+            my_s = v[u];
+            my_i = j;
+          }
         }
       }
     }
@@ -244,6 +254,254 @@ nms_v5_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
   for (int r = tid; r < max_out; r += kNmsThreads) {
     const int idx = r < nsel ? sel_idx[r] : 0;
     const float score = r < nsel ? sel_score[r] : 0.f;
+    const float4 b = bx[idx];
+    float* d = detections + (static_cast<size_t>(n) * max_out + r) * 7;
+    d[0] = static_cast<float>(image_id_base + n);
+    d[1] = __fmul_rn(fminf(fmaxf(b.x, 0.f), clip_h), scale_img);
+    d[2] = __fmul_rn(fminf(fmaxf(b.y, 0.f), clip_w), scale_img);
+    d[3] = __fmul_rn(fminf(fmaxf(b.z, 0.f), clip_h), scale_img);
+    d[4] = __fmul_rn(fminf(fmaxf(b.w, 0.f), clip_w), scale_img);
+    d[5] = score;
+    d[6] = static_cast<float>(classes[static_cast<size_t>(n) * k + idx] + 1);
+    sel_index[static_cast<size_t>(n) * max_out + r] = idx;
+  }
+  if (tid == 0) valid[n] = nsel;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Fast path: the same algorithm on the top candidates only, entirely in shared memory.
+//
+// Only the highest-scoring candidates are ever popped before max_output_size boxes are selected
+// (a few hundred for a 76 725-anchor image), so each image first compacts its top <= kFastCap
+// candidates into shared memory (adaptive histogram threshold on the score bits), then runs the
+// exact lazy-suppression loop there.  Exactness is PROVEN per image at run time: every popped
+// (stale) score must be strictly greater than the best excluded score; otherwise the image is
+// flagged and the full-queue kernel above recomputes it.
+// ------------------------------------------------------------------------------------------
+constexpr int kFastThreads = 256;
+constexpr int kFastCap = 4096;
+constexpr int kFastPer = kFastCap / kFastThreads;  // 16 slots per thread
+constexpr int kFastBins = 2048;
+
+__device__ __forceinline__ uint32_t score_key(float s) {
+  const uint32_t b = __float_as_uint(s);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // monotone float -> uint
+}
+
+struct FastSmem {
+  float4 box[kFastCap];
+  float score[kFastCap];
+  int idx[kFastCap];
+  unsigned short begin[kFastCap];
+  int hist[kFastBins];
+  float4 sel_box[kNmsMaxOut];
+  int sel_idx[kNmsMaxOut];
+  float sel_score[kNmsMaxOut];
+  float sim[kNmsMaxOut];
+  float wgt[kNmsMaxOut];
+  float red_s[kFastThreads / 32];
+  int red_i[kFastThreads / 32];
+  int red_slot[kFastThreads / 32];
+  uint32_t kmin, kmax;
+  int count, nsel, bstar, fail;
+  float excl_max;
+};
+
+__global__ void __launch_bounds__(kFastThreads)
+nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                   const int32_t* __restrict__ classes, const float* __restrict__ image_scales,
+                   int image_id_base, int k, int max_out, float iou_thr, float score_thr,
+                   float sigma, float clip_h, float clip_w, float* __restrict__ detections,
+                   int32_t* __restrict__ sel_index, int32_t* __restrict__ valid,
+                   int32_t* __restrict__ need_full) {
+  extern __shared__ __align__(16) uint8_t fast_raw[];
+  FastSmem& sm = *reinterpret_cast<FastSmem*>(fast_raw);
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float4* bx = reinterpret_cast<const float4*>(boxes) + static_cast<size_t>(n) * k;
+  const float* sc = scores + static_cast<size_t>(n) * k;
+  const bool soft = sigma > 0.f;
+  const float scale = soft ? __fdiv_rn(-0.5f, sigma) : 0.f;
+
+  // ---- A. key range of the valid candidates ----
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
+  for (int i = tid; i < k; i += kFastThreads) {
+    const float s = sc[i];
+    if (s > score_thr) {
+      const uint32_t key = score_key(s);
+      kmin = min(kmin, key);
+      kmax = max(kmax, key);
+    }
+  }
+  if (tid == 0) {
+    sm.kmin = 0xffffffffu; sm.kmax = 0u; sm.count = 0; sm.nsel = 0; sm.fail = 0;
+    sm.excl_max = -CUDART_INF_F; sm.bstar = 0;
+  }
+  for (int i = tid; i < kFastBins; i += kFastThreads) sm.hist[i] = 0;
+  __syncthreads();
+  atomicMin(&sm.kmin, kmin);
+  atomicMax(&sm.kmax, kmax);
+  __syncthreads();
+  kmin = sm.kmin; kmax = sm.kmax;
+  const bool any_valid = kmax >= kmin;
+  const unsigned long long range = any_valid ? static_cast<unsigned long long>(kmax - kmin) + 1ull : 1ull;
+  auto bin_of = [&](uint32_t key) -> int {
+    return static_cast<int>((static_cast<unsigned long long>(key - kmin) * kFastBins) / range);
+  };
+  // ---- B. histogram, C. threshold bin ----
+  if (any_valid) {
+    for (int i = tid; i < k; i += kFastThreads) {
+      const float s = sc[i];
+      if (s > score_thr) atomicAdd(&sm.hist[bin_of(score_key(s))], 1);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0, b = kFastBins;
+    while (b > 0 && acc + sm.hist[b - 1] <= kFastCap) acc += sm.hist[--b];
+    sm.bstar = b;
+    if (any_valid && acc == 0) sm.fail = 1;   // the top bin alone overflows the capacity
+  }
+  __syncthreads();
+  const int bstar = sm.bstar;
+  // ---- D. compaction into shared memory; best excluded score ----
+  float excl = -CUDART_INF_F;
+  if (any_valid && !sm.fail) {
+    for (int i = tid; i < k; i += kFastThreads) {
+      const float s = sc[i];
+      if (s > score_thr) {
+        if (bin_of(score_key(s)) >= bstar) {
+          const int slot = atomicAdd(&sm.count, 1);
+          sm.score[slot] = s;
+          sm.idx[slot] = i;
+          sm.begin[slot] = 0;
+          sm.box[slot] = bx[i];
+        } else {
+          excl = fmaxf(excl, s);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) excl = fmaxf(excl, __shfl_xor_sync(0xffffffffu, excl, o));
+  if (lane == 0) sm.red_s[warp] = excl;
+  __syncthreads();
+  if (tid == 0) {
+    float e = -CUDART_INF_F;
+    for (int w = 0; w < kFastThreads / 32; ++w) e = fmaxf(e, sm.red_s[w]);
+    sm.excl_max = e;
+  }
+  __syncthreads();
+  const int count = sm.count;
+  const float excl_max = sm.excl_max;
+  for (int sl = count + tid; sl < kFastCap; sl += kFastThreads) sm.score[sl] = -CUDART_INF_F;
+  __syncthreads();
+
+  // thread-local best over its interleaved slots (slot = tid + u * kFastThreads)
+  float my_s = -CUDART_INF_F;
+  int my_i = 0x7fffffff, my_slot = -1;
+  auto rescan = [&]() {
+    my_s = -CUDART_INF_F; my_i = 0x7fffffff; my_slot = -1;
+#pragma unroll
+    for (int u = 0; u < kFastPer; ++u) {
+      const int sl = tid + u * kFastThreads;
+      const float v = sm.score[sl];
+      if (v > -CUDART_INF_F) {
+        const int id = sm.idx[sl];
+        if (better(v, id, my_s, my_i)) { my_s = v; my_i = id; my_slot = sl; }
+      }
+    }
+  };
+  rescan();
+
+  // ---- E. exact lazy-suppression loop ----
+  while (!sm.fail) {
+    const int nsel = sm.nsel;   // stable here: only written between the two barriers below
+    float s = my_s;
+    int i = my_i, slot = my_slot;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float so = __shfl_xor_sync(0xffffffffu, s, o);
+      const int io = __shfl_xor_sync(0xffffffffu, i, o);
+      const int lo = __shfl_xor_sync(0xffffffffu, slot, o);
+      if (better(so, io, s, i)) { s = so; i = io; slot = lo; }
+    }
+    if (lane == 0) { sm.red_s[warp] = s; sm.red_i[warp] = i; sm.red_slot[warp] = slot; }
+    __syncthreads();
+    // every warp reduces the 8 partials itself: no second barrier for the broadcast
+    s = lane < kFastThreads / 32 ? sm.red_s[lane] : -CUDART_INF_F;
+    i = lane < kFastThreads / 32 ? sm.red_i[lane] : 0x7fffffff;
+    slot = lane < kFastThreads / 32 ? sm.red_slot[lane] : -1;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float so = __shfl_xor_sync(0xffffffffu, s, o);
+      const int io = __shfl_xor_sync(0xffffffffu, i, o);
+      const int lo = __shfl_xor_sync(0xffffffffu, slot, o);
+      if (better(so, io, s, i)) { s = so; i = io; slot = lo; }
+    }
+    s = __shfl_sync(0xffffffffu, s, 0);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (nsel >= max_out) break;
+    if (s == -CUDART_INF_F) {           // queue exhausted
+      if (excl_max > -CUDART_INF_F) { if (tid == 0) sm.fail = 1; __syncthreads(); }
+      break;
+    }
+    if (!(s > excl_max)) {              // an excluded candidate could be next: not provable
+      if (tid == 0) sm.fail = 1;
+      __syncthreads();
+      break;
+    }
+    const int owner = slot % kFastThreads;
+    if (warp == (owner >> 5)) {
+      const int begin = sm.begin[slot];
+      const float4 cb = sm.box[slot];
+      for (int j = begin + lane; j < nsel; j += 32) {
+        const float simv = iou_tf(cb, sm.sel_box[j]);
+        float wgt = static_cast<float>(exp(static_cast<double>(__fmul_rn(__fmul_rn(scale, simv), simv))));
+        if (!(soft || simv <= iou_thr)) wgt = 0.f;
+        sm.sim[j] = simv;
+        sm.wgt[j] = wgt;
+      }
+      __syncwarp();
+      if (tid == owner) {
+        float cur = s;
+        bool hard = false;
+        for (int j = nsel - 1; j >= begin; --j) {
+          cur = __fmul_rn(cur, sm.wgt[j]);
+          if (!soft && sm.sim[j] > iou_thr) { hard = true; break; }
+          if (cur <= score_thr) break;
+        }
+        float new_s = -CUDART_INF_F;
+        if (!hard) {
+          if (cur == s) {
+            sm.sel_box[nsel] = cb;
+            sm.sel_idx[nsel] = i;
+            sm.sel_score[nsel] = cur;
+            sm.nsel = nsel + 1;
+          } else if (cur > score_thr) {
+            new_s = cur;
+            sm.begin[slot] = static_cast<unsigned short>(nsel);
+          }
+        }
+        sm.score[slot] = new_s;
+        rescan();
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (sm.fail) {
+    if (tid == 0) need_full[n] = 1;
+    return;
+  }
+  if (tid == 0) need_full[n] = 0;
+  const int nsel = sm.nsel;
+  const float scale_img = image_scales ? image_scales[n] : 1.f;
+  for (int r = tid; r < max_out; r += kFastThreads) {
+    const int idx = r < nsel ? sm.sel_idx[r] : 0;
+    const float score = r < nsel ? sm.sel_score[r] : 0.f;
     const float4 b = bx[idx];
     float* d = detections + (static_cast<size_t>(n) * max_out + r) * 7;
     d[0] = static_cast<float>(image_id_base + n);
@@ -300,7 +558,7 @@ extern "C" int edet_pre_nms(const edet_half* const* h_cls, const edet_half* cons
 }
 
 extern "C" size_t edet_nms_work_bytes(int n, int k) {
-  return static_cast<size_t>(n) * k * (sizeof(float) + sizeof(int32_t));
+  return static_cast<size_t>(n) * k * (sizeof(float) + sizeof(int32_t)) + static_cast<size_t>(n) * sizeof(int32_t);
 }
 
 extern "C" int edet_nms_v5(const float* boxes, const float* scores, const int32_t* classes,
@@ -316,9 +574,24 @@ extern "C" int edet_nms_v5(const float* boxes, const float* scores, const int32_
                  "nms_v5: max_output_size must be in 1..%d", kNmsMaxOut);
   float* ws = reinterpret_cast<float*>(work);
   int32_t* wb = reinterpret_cast<int32_t*>(ws + static_cast<size_t>(n) * k);
+  int32_t* need_full = wb + static_cast<size_t>(n) * k;
+  static bool configured = false;
+  if (!configured) {
+    EDET_CHECK_CUDA(cudaFuncSetAttribute(nms_v5_fast_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(sizeof(FastSmem))));
+    configured = true;
+  }
+  // fast path (top candidates in shared memory, exactness proven per image) ...
+  nms_v5_fast_kernel<<<n, kFastThreads, sizeof(FastSmem), as_stream(stream)>>>(
+      boxes, scores, classes, image_scales, image_id_base, k, max_output_size, iou_threshold,
+      score_threshold, soft_nms_sigma, clip_h, clip_w, detections, sel_index, valid, need_full);
+  EDET_CHECK_LAUNCH();
+  // ... and the full-queue kernel, which returns immediately for images the fast path settled.
   nms_v5_kernel<<<n, kNmsThreads, 0, as_stream(stream)>>>(
       boxes, scores, classes, image_scales, image_id_base, k, max_output_size, iou_threshold,
-      score_threshold, soft_nms_sigma, clip_h, clip_w, detections, sel_index, valid, ws, wb);
+      score_threshold, soft_nms_sigma, clip_h, clip_w, detections, sel_index, valid, ws, wb,
+      need_full);
   EDET_CHECK_LAUNCH();
   return EDET_OK;
 }

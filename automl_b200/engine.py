@@ -221,9 +221,14 @@ class Engine(object):
       src = pyramid[r.src]
       if r.has_conv:
         src = resample_conv(r, src)
-      out = self._buf(r.scope, (n, r.out_hw[0], r.out_hw[1], F))
+      if r.mode == 'same':
+        # 1x1 maps cannot shrink further: the reference only applies the (optional) 1x1 conv
+        # (efficientdet_arch.py:116-117), so the level aliases its source.
+        pyramid.append(src)
+        continue
       if r.mode != 'down':
-        raise NotImplementedError('extra level that is not a downsample')
+        raise NotImplementedError('extra level that is an upsample')
+      out = self._buf(r.scope, (n, r.out_hw[0], r.out_hw[1], F))
       self._add(r.scope + '/pool',
                 lambda src=src, out=out, r=r: ops.max_pool(src, out, r.pool[:2], r.pool[2:]),
                 kind='max_pool', nbytes=2 * (src.numel() + out.numel()))

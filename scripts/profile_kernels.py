@@ -1,0 +1,47 @@
+"""Launches representative kernels of the D0@640 batch-32 step stand-alone (for `ncu --set full`).
+Usage: python scripts/profile_kernels.py [reps]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from automl_b200 import ops, utils  # noqa: E402
+
+dev = 'cuda:0'
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+N = 32
+
+
+def dw(h, c, k, s, se=True):
+  x = torch.randn(N, h, h, c, device=dev).half()
+  w = torch.randn(k * k, c, device=dev).half()
+  b = torch.randn(c, device=dev)
+  ho = -(-h // s)
+  out = torch.empty(N, ho, ho, c, dtype=torch.float16, device=dev)
+  part = torch.empty(N, ops.depthwise_tiles(h, h, c, k, s), c, device=dev) if se else None
+  for _ in range(reps):
+    ops.depthwise_conv(x, out, w, b, utils.ACT_SWISH, k, s, part)
+
+
+def pw(m, k, n, act, res=False, per_image=False):
+  a = torch.randn(N, m // N, k, device=dev).half()
+  w = (torch.randn(N if per_image else 1, n, k, device=dev) / k**0.5).half()
+  b = torch.randn(n, device=dev)
+  out = torch.empty(N, m // N, (n + 7) // 8 * 8, dtype=torch.float16, device=dev)
+  r = torch.randn_like(out) if res else None
+  for _ in range(reps):
+    ops.pointwise_conv(a, w, b, out, act, residual=r, rows=m // N, batch=N, nout=n)
+
+
+dw(320, 32, 3, 1)          # blocks_0 dw
+dw(320, 96, 3, 2)          # blocks_1 dw (largest byte mover)
+dw(80, 240, 5, 1)          # blocks_4 dw
+dw(40, 672, 5, 1)          # blocks_9 dw
+pw(3276800, 16, 96, utils.ACT_SWISH)                 # blocks_1 expand
+pw(819200, 144, 24, utils.ACT_NONE, res=True, per_image=True)   # blocks_2 project
+pw(51200, 80, 480, utils.ACT_SWISH)                  # blocks_6 expand
+pw(12800, 1152, 192, utils.ACT_NONE, res=True, per_image=True)  # blocks_12 project
+pw(204800, 64, 810, utils.ACT_NONE)                  # class-predict L3
+torch.cuda.synchronize()
+print('done')
