@@ -33,12 +33,11 @@ SIGNATURES = {
     'edet_pointwise_conv': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                     c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]),
-    'edet_depthwise_tiles': (c_int, [c_int, c_int, c_int, c_int, c_int]),
     'edet_depthwise_conv': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    'edet_se_fc': (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+    'edet_se_fc': (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                           c_void_p]),
+                           c_int, c_void_p]),
     'edet_fuse_dw': (c_int, [ctypes.POINTER(FuseInput), c_int, c_void_p, c_void_p, c_int, c_int,
                              c_int, c_int, c_int, c_void_p]),
     'edet_max_pool': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,

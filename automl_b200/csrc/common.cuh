@@ -69,6 +69,23 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+// Activation on a pair of values with the packed fp32 pipe of sm_100 (FADD2 / FMUL2 / FFMA2):
+// halves the ALU issue slots of the swish epilogues; the two MUFU ops per element remain.
+template <int ACT>
+__device__ __forceinline__ float2 apply_act2(float2 x) {
+  if (ACT == EDET_ACT_SWISH) {
+    const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+    float2 e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+    const float2 d = __fadd2_rn(e, make_float2(1.f, 1.f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));   // rcp(inf) = 0: x -> -0 for x << 0
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+    return __fmul2_rn(x, r);
+  }
+  return make_float2(apply_act_t<ACT>(x.x), apply_act_t<ACT>(x.y));
+}
+
 // 8 halves <-> 8 floats through one 128-bit register quad.
 struct alignas(16) Half8 {
   __half2 h[4];

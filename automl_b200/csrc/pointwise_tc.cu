@@ -10,9 +10,11 @@
 //   warp 1      : allocates TMEM, then one lane issues tcgen05.mma (kind::f16, M=128,
 //                 N=block_n, K=16) with fp32 accumulators in TMEM, double-buffered across tiles;
 //                 tcgen05.commit releases smem stages / publishes the accumulator.
-//   warps 2..5  : epilogue -- tcgen05.ld (32x32b) -> +bias -> activation -> (+residual) -> fp16 ->
+//   warps 2..9  : epilogue -- tcgen05.ld (32x32b) -> +bias -> activation -> (+residual) -> fp16 ->
 //                 swizzled st.shared -> TMA store (cp.async.bulk.tensor ... bulk_group), which
-//                 also clips the ragged M / N edges.
+//                 also clips the ragged M / N edges.  Two warps share each TMEM lane quarter and
+//                 split every 64-column store chunk into two 32-column halves (the swish
+//                 epilogue is MUFU / issue bound, so it gets 8 warps and packed fp32 math).
 //
 // Replaces Conv2D 1x1 (+BN, +swish, +skip) at the reference call sites listed in
 // include/automl_b200.h (edet_pointwise_conv).  Algorithmic HBM bytes per launch:
@@ -27,8 +29,8 @@ namespace pwtc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 halves = 128 bytes = one 128B-swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kEpiThreads = 256;
 constexpr int kStoreStages = 2;
 constexpr int kStoreCols = 64;
 constexpr int kATileBytes = BLOCK_M * BLOCK_K * 2;        // 16 KiB
@@ -194,7 +196,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[s]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tmem_empty_bar[s]), kEpiThreads / 32);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -277,9 +279,10 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       }
     }
   } else {
-    // ===================== Epilogue (warps 2..5) =====================
-    const int e_tid = threadIdx.x - 64;       // 0..127
+    // ===================== Epilogue (warps 2..9) =====================
+    const int e_tid = threadIdx.x - 64;       // 0..255
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int half_id = (warp - 2) >> 2;      // which 32-column half of a store chunk
     const int row_in_tile = quarter * 32 + lane;
     int iter = 0;
     int store_iter = 0;
@@ -311,12 +314,13 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
         uint8_t* stage_buf = smem_store + sb * kStoreBytes;
         if (e_tid == 0) tma_store_wait_read<kStoreStages - 1>();
         epi_barrier();  // staging buffer free; bias_s visible
-        float v[64];
+        const int c_lo = half_id * 32;            // this warp's columns inside the chunk
+        float v[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>(as * p.block_n + c * kStoreCols);
+                               static_cast<uint32_t>(as * p.block_n + c * kStoreCols + c_lo);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g * 16 < cols) tc_ld16(taddr + g * 16, v + g * 16);
+        for (int g = 0; g < 2; ++g) {
+          if (c_lo + g * 16 < cols) tc_ld16(taddr + g * 16, v + g * 16);
         }
         tc_wait_ld();
         if (c == num_chunks - 1) {
@@ -327,16 +331,19 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
         }
         uint8_t* row_base = stage_buf + row_in_tile * 128;
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          if (jj * 8 < cols) {
-            float o[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c * kStoreCols + jj * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c * kStoreCols + jj * 8 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = apply_act_t<ACT>(v[jj * 8 + e] + bb[e]);
+        for (int jj = 0; jj < 4; ++jj) {
+          if (c_lo + jj * 8 < cols) {
+            const float* bsrc = bias_s + c * kStoreCols + c_lo + jj * 8;
+            const float4 b0 = *reinterpret_cast<const float4*>(bsrc);
+            const float4 b1 = *reinterpret_cast<const float4*>(bsrc + 4);
+            float2 o2[4];
+            o2[0] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 0], v[jj * 8 + 1]), make_float2(b0.x, b0.y)));
+            o2[1] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 2], v[jj * 8 + 3]), make_float2(b0.z, b0.w)));
+            o2[2] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 4], v[jj * 8 + 5]), make_float2(b1.x, b1.y)));
+            o2[3] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 6], v[jj * 8 + 7]), make_float2(b1.z, b1.w)));
+            float o[8] = {o2[0].x, o2[0].y, o2[1].x, o2[1].y, o2[2].x, o2[2].y, o2[3].x, o2[3].y};
             if (HAS_RES) {
-              const int col = n0 + c * kStoreCols + jj * 8;
+              const int col = n0 + c * kStoreCols + c_lo + jj * 8;
               if (row_ok && col < p.nout) {
                 float r[8];
                 half8_to_float(ldg_nc_v4(res_row + col), r);
@@ -345,7 +352,8 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
               }
             }
             const uint4 packed = float_to_half8(o);
-            *reinterpret_cast<uint4*>(row_base + ((jj ^ (row_in_tile & 7)) << 4)) = packed;
+            const int chunk16 = half_id * 4 + jj;   // 16-byte piece inside the 128-byte row
+            *reinterpret_cast<uint4*>(row_base + ((chunk16 ^ (row_in_tile & 7)) << 4)) = packed;
           }
         }
         fence_proxy_async_smem();

@@ -274,15 +274,17 @@ nms_v5_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
 //
 // Only the highest-scoring candidates are ever popped before max_output_size boxes are selected
 // (a few hundred for a 76 725-anchor image), so each image first compacts its top <= kFastCap
-// candidates into shared memory (adaptive histogram threshold on the score bits), then runs the
+// candidates into shared memory (adaptive two-level histogram threshold on the score bits; the
+// boxes stay in global memory and are fetched when a candidate is popped), then runs the
 // exact lazy-suppression loop there.  Exactness is PROVEN per image at run time: every popped
 // (stale) score must be strictly greater than the best excluded score; otherwise the image is
 // flagged and the full-queue kernel above recomputes it.
 // ------------------------------------------------------------------------------------------
-constexpr int kFastThreads = 256;
-constexpr int kFastCap = 4096;
-constexpr int kFastPer = kFastCap / kFastThreads;  // 16 slots per thread
+constexpr int kFastThreads = 512;
+constexpr int kFastCap = 16384;
+constexpr int kFastPer = kFastCap / kFastThreads;  // 32 slots per thread
 constexpr int kFastBins = 2048;
+constexpr int kFastWarps = kFastThreads / 32;
 
 __device__ __forceinline__ uint32_t score_key(float s) {
   const uint32_t b = __float_as_uint(s);
@@ -290,7 +292,6 @@ __device__ __forceinline__ uint32_t score_key(float s) {
 }
 
 struct FastSmem {
-  float4 box[kFastCap];
   float score[kFastCap];
   int idx[kFastCap];
   unsigned short begin[kFastCap];
@@ -300,11 +301,11 @@ struct FastSmem {
   float sel_score[kNmsMaxOut];
   float sim[kNmsMaxOut];
   float wgt[kNmsMaxOut];
-  float red_s[kFastThreads / 32];
-  int red_i[kFastThreads / 32];
-  int red_slot[kFastThreads / 32];
+  float red_s[kFastWarps];
+  int red_i[kFastWarps];
+  int red_slot[kFastWarps];
   uint32_t kmin, kmax;
-  int count, nsel, bstar, fail;
+  int count, nsel, bstar, sstar, fail;
   float excl_max;
 };
 
@@ -336,7 +337,7 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
   }
   if (tid == 0) {
     sm.kmin = 0xffffffffu; sm.kmax = 0u; sm.count = 0; sm.nsel = 0; sm.fail = 0;
-    sm.excl_max = -CUDART_INF_F; sm.bstar = 0;
+    sm.excl_max = -CUDART_INF_F; sm.bstar = 0; sm.sstar = 0;
   }
   for (int i = tid; i < kFastBins; i += kFastThreads) sm.hist[i] = 0;
   __syncthreads();
@@ -345,38 +346,73 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
   __syncthreads();
   kmin = sm.kmin; kmax = sm.kmax;
   const bool any_valid = kmax >= kmin;
-  const unsigned long long range = any_valid ? static_cast<unsigned long long>(kmax - kmin) + 1ull : 1ull;
-  auto bin_of = [&](uint32_t key) -> int {
-    return static_cast<int>((static_cast<unsigned long long>(key - kmin) * kFastBins) / range);
+  // bin = floor((key - kmin) * inv) in [0, kFastBins); the fraction inside the bin gives a
+  // second-level sub-bin.  Both are monotone in the key, which is all the selection needs.
+  const double inv = static_cast<double>(kFastBins) /
+                     (static_cast<double>(any_valid ? kmax - kmin : 0u) + 1.0);
+  auto bin_of = [&](uint32_t key, int& sub) -> int {
+    const double x = static_cast<double>(key - kmin) * inv;
+    int b = static_cast<int>(x);
+    b = b > kFastBins - 1 ? kFastBins - 1 : b;
+    int sb = static_cast<int>((x - static_cast<double>(b)) * kFastBins);
+    sub = sb > kFastBins - 1 ? kFastBins - 1 : (sb < 0 ? 0 : sb);
+    return b;
   };
-  // ---- B. histogram, C. threshold bin ----
+  // ---- B. coarse histogram -> threshold bin ----
   if (any_valid) {
     for (int i = tid; i < k; i += kFastThreads) {
       const float s = sc[i];
-      if (s > score_thr) atomicAdd(&sm.hist[bin_of(score_key(s))], 1);
+      int sub;
+      if (s > score_thr) atomicAdd(&sm.hist[bin_of(score_key(s), sub)], 1);
     }
   }
   __syncthreads();
   if (tid == 0) {
     int acc = 0, b = kFastBins;
     while (b > 0 && acc + sm.hist[b - 1] <= kFastCap) acc += sm.hist[--b];
-    sm.bstar = b;
-    if (any_valid && acc == 0) sm.fail = 1;   // the top bin alone overflows the capacity
+    sm.bstar = b;       // bins >= bstar are taken whole; bin bstar-1 is refined below
+    sm.count = acc;     // (reused as the running total for the refinement)
   }
   __syncthreads();
   const int bstar = sm.bstar;
+  const int coarse_total = sm.count;
+  __syncthreads();
+  // ---- B2. refine the boundary bin with a second-level histogram ----
+  for (int i = tid; i < kFastBins; i += kFastThreads) sm.hist[i] = 0;
+  __syncthreads();
+  if (any_valid && bstar > 0) {
+    for (int i = tid; i < k; i += kFastThreads) {
+      const float s = sc[i];
+      if (s > score_thr) {
+        int sub;
+        if (bin_of(score_key(s), sub) == bstar - 1) atomicAdd(&sm.hist[sub], 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = coarse_total, sb = kFastBins;
+    if (bstar > 0)
+      while (sb > 0 && acc + sm.hist[sb - 1] <= kFastCap) acc += sm.hist[--sb];
+    sm.sstar = sb;
+    sm.count = 0;
+    if (any_valid && acc == 0) sm.fail = 1;  // one score value alone overflows the capacity
+  }
+  __syncthreads();
+  const int sstar = sm.sstar;
   // ---- D. compaction into shared memory; best excluded score ----
   float excl = -CUDART_INF_F;
   if (any_valid && !sm.fail) {
     for (int i = tid; i < k; i += kFastThreads) {
       const float s = sc[i];
       if (s > score_thr) {
-        if (bin_of(score_key(s)) >= bstar) {
+        int sub;
+        const int b = bin_of(score_key(s), sub);
+        if (b >= bstar || (b == bstar - 1 && sub >= sstar)) {
           const int slot = atomicAdd(&sm.count, 1);
           sm.score[slot] = s;
           sm.idx[slot] = i;
           sm.begin[slot] = 0;
-          sm.box[slot] = bx[i];
         } else {
           excl = fmaxf(excl, s);
         }
@@ -389,7 +425,7 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
   __syncthreads();
   if (tid == 0) {
     float e = -CUDART_INF_F;
-    for (int w = 0; w < kFastThreads / 32; ++w) e = fmaxf(e, sm.red_s[w]);
+    for (int w = 0; w < kFastWarps; ++w) e = fmaxf(e, sm.red_s[w]);
     sm.excl_max = e;
   }
   __syncthreads();
@@ -403,7 +439,7 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
   int my_i = 0x7fffffff, my_slot = -1;
   auto rescan = [&]() {
     my_s = -CUDART_INF_F; my_i = 0x7fffffff; my_slot = -1;
-#pragma unroll
+#pragma unroll 8
     for (int u = 0; u < kFastPer; ++u) {
       const int sl = tid + u * kFastThreads;
       const float v = sm.score[sl];
@@ -429,12 +465,12 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
     }
     if (lane == 0) { sm.red_s[warp] = s; sm.red_i[warp] = i; sm.red_slot[warp] = slot; }
     __syncthreads();
-    // every warp reduces the 8 partials itself: no second barrier for the broadcast
-    s = lane < kFastThreads / 32 ? sm.red_s[lane] : -CUDART_INF_F;
-    i = lane < kFastThreads / 32 ? sm.red_i[lane] : 0x7fffffff;
-    slot = lane < kFastThreads / 32 ? sm.red_slot[lane] : -1;
+    // every warp reduces the per-warp partials itself: no second barrier for the broadcast
+    s = lane < kFastWarps ? sm.red_s[lane] : -CUDART_INF_F;
+    i = lane < kFastWarps ? sm.red_i[lane] : 0x7fffffff;
+    slot = lane < kFastWarps ? sm.red_slot[lane] : -1;
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
+    for (int o = kFastWarps / 2; o > 0; o >>= 1) {
       const float so = __shfl_xor_sync(0xffffffffu, s, o);
       const int io = __shfl_xor_sync(0xffffffffu, i, o);
       const int lo = __shfl_xor_sync(0xffffffffu, slot, o);
@@ -445,18 +481,18 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if (nsel >= max_out) break;
     if (s == -CUDART_INF_F) {           // queue exhausted
-      if (excl_max > -CUDART_INF_F) { if (tid == 0) sm.fail = 1; __syncthreads(); }
+      if (excl_max > -CUDART_INF_F) { if (tid == 0) sm.fail = 2; __syncthreads(); }
       break;
     }
     if (!(s > excl_max)) {              // an excluded candidate could be next: not provable
-      if (tid == 0) sm.fail = 1;
+      if (tid == 0) sm.fail = 3;
       __syncthreads();
       break;
     }
     const int owner = slot % kFastThreads;
     if (warp == (owner >> 5)) {
       const int begin = sm.begin[slot];
-      const float4 cb = sm.box[slot];
+      const float4 cb = bx[i];
       for (int j = begin + lane; j < nsel; j += 32) {
         const float simv = iou_tf(cb, sm.sel_box[j]);
         float wgt = static_cast<float>(exp(static_cast<double>(__fmul_rn(__fmul_rn(scale, simv), simv))));
@@ -493,7 +529,7 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
   }
   __syncthreads();
   if (sm.fail) {
-    if (tid == 0) need_full[n] = 1;
+    if (tid == 0) need_full[n] = sm.fail;   // reason code (1: tie overflow, 2: exhausted, 3: bound)
     return;
   }
   if (tid == 0) need_full[n] = 0;

@@ -135,6 +135,14 @@ class Engine(object):
 
     # -- MBConv blocks ----------------------------------------------------------------------
     feats = {}
+    max_mid = max(b.mid_filters for b in a.blocks)
+    se_acc = [self._buf('se_acc%d' % i, (n, max_mid), torch.int64) for i in range(2)]
+    for t in se_acc:
+      t.zero_()
+    se_index = 0
+    if any(b.se_filters for b in a.blocks):
+      # one explicit clear per forward keeps the ping-pong valid for any number of SE blocks
+      self._add('se_clear', lambda t=se_acc[0]: t.zero_(), kind='memset', nbytes=8 * n * max_mid)
     for b in a.blocks:
       scope = '%s/%s' % (bb, b.name)
       check_c(b.input_filters, scope); check_c(b.mid_filters, scope); check_c(b.output_filters, scope)
@@ -157,14 +165,17 @@ class Engine(object):
       dwo = self._buf(b.name + '/dw', (n, ho, wo, b.mid_filters))
       partial = None
       if b.se_filters:
-        tiles = ops.depthwise_tiles(h, wd, b.mid_filters, b.kernel_size, b.stride)
-        partial = self._buf(b.name + '/se_partial', (n, tiles, b.mid_filters), f32)
+        # int64 fixed-point squeeze accumulator [n, mid]; two buffers alternate between blocks,
+        # each block's se_fc launch clears the one the next block will accumulate into.
+        partial = se_acc[se_index % 2].view(-1)[:n * b.mid_filters].view(n, b.mid_filters)
+        next_zero = se_acc[(se_index + 1) % 2]
+        se_index += 1
       self._add(b.name + '/dw',
                 lambda mid=mid, dwo=dwo, dw_w=dw_w, dw_b=dw_b, partial=partial, b=b:
                 ops.depthwise_conv(mid, dwo, dw_w, dw_b, act, b.kernel_size, b.stride, partial),
                 kind='depthwise_k%ds%d' % (b.kernel_size, b.stride),
                 nbytes=2 * n * b.mid_filters * (h * wd + ho * wo) + 2 * b.kernel_size**2 * b.mid_filters
-                + (4 * partial.numel() if partial is not None else 0),
+                + (8 * partial.numel() if partial is not None else 0),
                 flops=2 * b.kernel_size**2 * n * b.mid_filters * ho * wo)
       # project (+SE folded into per-image weights, + skip)
       s, sh = _bn_fold(w, '%s/%s' % (scope, b.project_bn), eps)
@@ -183,9 +194,10 @@ class Engine(object):
         inv_hw = 1.0 / float(ho * wo)
         self._add(b.name + '/se',
                   lambda partial=partial, inv_hw=inv_hw, w1=w1, b1=b1, w2=w2, b2=b2, gate=gate,
-                  proj_wt=proj_wt, wt_scaled=wt_scaled:
-                  ops.se_fc(partial, inv_hw, w1, b1, w2, b2, gate, act, proj_wt, wt_scaled),
-                  kind='se_fc', nbytes=4 * partial.numel() + 2 * proj_wt.numel() + 2 * wt_scaled.numel())
+                  proj_wt=proj_wt, wt_scaled=wt_scaled, next_zero=next_zero:
+                  ops.se_fc(partial, inv_hw, w1, b1, w2, b2, gate, act, proj_wt, wt_scaled,
+                            next_zero),
+                  kind='se_fc', nbytes=8 * partial.numel() + 2 * proj_wt.numel() + 2 * wt_scaled.numel())
         self._pw(b.name + '/project', dwo, wt_scaled, proj_b, y, utils.ACT_NONE, residual=res,
                  batch=n, rows=ho * wo)
       else:
@@ -405,6 +417,11 @@ class Engine(object):
         self.image_scales.copy_(torch.as_tensor(image_scales, dtype=torch.float32), non_blocking=True)
       self.run(postprocess=True)
     return self.detections
+
+  def nms_fallback_count(self):
+    """Images of the last run that needed the full-queue NMS kernel (fast path not provable)."""
+    flags = self.buffers['nms_work'][-4 * self.n:].view(torch.int32)
+    return int(flags.sum().item())
 
   def op_names(self):
     return [n for n, _ in self._ops]

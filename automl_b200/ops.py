@@ -55,25 +55,25 @@ def pointwise_conv(a, wt, bias, out, act, residual=None, rows=None, batch=None, 
             _ptr(out, torch.float16), ldo, batch, rows, k, n_out, act, impl, _stream())
 
 
-def depthwise_tiles(h, w, c, k, stride):
-  return _lib.load().edet_depthwise_tiles(h, w, c, k, stride)
-
-
-def depthwise_conv(x, out, w, bias, act, k, stride, se_partial=None):
+def depthwise_conv(x, out, w, bias, act, k, stride, se_sum=None):
+  """se_sum: int64 [N, C] accumulator (added to; 2^-20 fixed point) or None."""
   n, h, wd, c = x.shape
   _lib.call('edet_depthwise_conv', _ptr(x, torch.float16), _ptr(out, torch.float16),
-            _ptr(w, torch.float16), _ptr(bias, torch.float32), _ptr(se_partial, torch.float32),
+            _ptr(w, torch.float16), _ptr(bias, torch.float32), _ptr(se_sum, torch.int64),
             n, h, wd, c, k, stride, act, _stream())
 
 
-def se_fc(partial, inv_hw, w1, b1, w2, b2, gate, act, wt=None, wt_scaled=None):
-  n, tiles, c = partial.shape
+def se_fc(se_sum, inv_hw, w1, b1, w2, b2, gate, act, wt=None, wt_scaled=None, zero_buf=None):
+  """se_sum int64 [N, C]; zero_buf: int64 [N, Cz] buffer cleared by the same launch."""
+  n, c = gate.shape
   se = w1.shape[0]
   nout = wt.shape[0] if wt is not None else 0
-  _lib.call('edet_se_fc', _ptr(partial, torch.float32), tiles, ctypes.c_float(inv_hw),
+  zc = zero_buf.shape[1] if zero_buf is not None else 0
+  _lib.call('edet_se_fc', _ptr(se_sum, torch.int64), ctypes.c_float(inv_hw),
             _ptr(w1, torch.float32), _ptr(b1, torch.float32), _ptr(w2, torch.float32),
             _ptr(b2, torch.float32), _ptr(gate, torch.float32), _ptr(wt, torch.float16),
-            _ptr(wt_scaled, torch.float16), n, c, se, nout, act, _stream())
+            _ptr(wt_scaled, torch.float16), _ptr(zero_buf, torch.int64), zc, n, c, se, nout, act,
+            _stream())
 
 
 def make_fuse_inputs(specs):

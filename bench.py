@@ -100,7 +100,7 @@ def cpu_baseline(config, weights, images, seconds_budget=25.0):
   import torch
   from oracle import efficientdet_oracle as eo
   from oracle import postprocess_oracle as po
-  cores = os.cpu_count() or 1
+  cores = min(os.cpu_count() or 1, 32)   # more threads than this slow the small convs down
   torch.set_num_threads(cores)
   orc = eo.Oracle(config, weights, torch.float32)
   params = config.as_dict()
@@ -281,7 +281,8 @@ def main():
                 'h2d_bytes_per_step': int(host_images.numel() * 4),
                 'd2h_bytes_per_step': int(host_det.numel() * 4),
                 'api': 'Engine.input <- pinned host fp32 images; Engine.run(); detections -> pinned host'},
-        'gpu_launches': eng.launches_per_forward * args.steps,
+        'gpu_launches': (eng.launches_per_forward + 1) * args.steps,
+        'nms_full_queue_images': eng.nms_fallback_count(),
         'clocks': clocks, 'roofline': roofline, 'cpu_baseline': base,
     }
     print(json.dumps(line))

@@ -90,32 +90,34 @@ int edet_pointwise_conv(const edet_half* a, int lda, const edet_half* wt, int wb
 
 /*
  * Depthwise k x k convolution 'same' (k in {3,5}, stride in {1,2}) + bias + act, optionally
- * emitting per-(image, tile, channel) partial sums of the activated output for the SE squeeze.
+ * accumulating the per-(image, channel) sum of the activated output for the SE squeeze.
  * Replaces DepthwiseConv2D + BN + swish  backbone/efficientnet_model.py:320-333, 391 and the
  * depthwise half of SeparableConv2D  efficientdet_arch.py:149-191, 206-249 (bias NULL, act NONE).
  *   in   half [n, h, w, c]     out  half [n, ceil(h/s), ceil(w/s), c]
  *   w    half [k*k][c] (BN scale folded)        bias float32 [c] or NULL
- *   se_partial  float32 [n, edet_depthwise_tiles(...), c] or NULL
+ *   se_sum  int64 [n, c] or NULL: ADDED to (caller zeroes it), 2^-20 fixed point, so the
+ *           reduction is order independent and bit-reproducible
  */
-int edet_depthwise_tiles(int h, int wd, int c, int k, int stride);
 int edet_depthwise_conv(const edet_half* in, edet_half* out, const edet_half* w,
-                        const float* bias, float* se_partial, int n, int h, int wd, int c, int k,
+                        const float* bias, int64_t* se_sum, int n, int h, int wd, int c, int k,
                         int stride, int act, edet_stream_t stream);
 
 /*
  * Squeeze-and-excitation gate, and the excitation folded into the project weights:
- *   mean = sum(partials) * inv_hw ; s = sigmoid(W2 @ act(W1 @ mean + b1) + b2)
+ *   mean = se_sum * 2^-20 * inv_hw ; s = sigmoid(W2 @ act(W1 @ mean + b1) + b2)
  *   wt_scaled[img, o, c] = wt[o, c] * s[img, c]
  * Replaces backbone/efficientnet_model.py:183-195 (SE.call) and the multiply at :195.
- *   partial  float32 [n, tiles, c]      w1 float32 [se][c], b1 [se], w2 float32 [c][se], b2 [c]
+ *   se_sum   int64 [n, c]               w1 float32 [se][c], b1 [se], w2 float32 [c][se], b2 [c]
  *   gate     float32 [n, c] (output, always written)
  *   wt       half [nout][c] project weights (nullable -> only the gate is produced)
  *   wt_scaled half [n][nout][c]
+ *   zero_buf int64 [n, zero_count] or NULL: cleared by this call (the accumulator of the next
+ *            block, so no separate memset launch is needed)
  */
-int edet_se_fc(const float* partial, int tiles, float inv_hw, const float* w1, const float* b1,
+int edet_se_fc(const int64_t* se_sum, float inv_hw, const float* w1, const float* b1,
                const float* w2, const float* b2, float* gate, const edet_half* wt,
-               edet_half* wt_scaled, int n, int c, int se, int nout, int act,
-               edet_stream_t stream);
+               edet_half* wt_scaled, int64_t* zero_buf, int zero_count, int n, int c, int se,
+               int nout, int act, edet_stream_t stream);
 
 /*
  * One BiFPN node in a single pass: per input {identity | TF1 nearest-neighbour upsample |

@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -2
+timeout 1200 python -m pytest tests -q -m gpu --timeout 300 2>&1 | tail -30 > gpurun_out/t_all.log; tail -8 gpurun_out/t_all.log
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --profile-out gpurun_out/ops_r1c.json > gpurun_out/bench3.log 2>&1; tail -2 gpurun_out/bench3.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1300 -c 700 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -1 gpurun_out/ncu_bench.log | cut -c1-300
+ls -la gpurun_out

@@ -107,8 +107,7 @@ def test_depthwise_conv(case):
   out = torch.empty(n, ho, wo, c, dtype=torch.float16, device=DEV)
   partial = None
   if has_se:
-    tiles = ops.depthwise_tiles(h, w, c, k, s)
-    partial = torch.full((n, tiles, c), float('nan'), device=DEV)
+    partial = torch.zeros(n, c, dtype=torch.int64, device=DEV)   # 2^-20 fixed-point sums
   ops.depthwise_conv(x.to(DEV), out, wk.reshape(k * k, c).to(DEV),
                      bias.to(DEV) if has_bias else None, act, k, s, partial)
   torch.cuda.synchronize()
@@ -120,25 +119,34 @@ def test_depthwise_conv(case):
   assert got.shape == ref.shape
   assert torch.allclose(got, ref, rtol=2e-3, atol=2e-3), float((got - ref).abs().max())
   if has_se:
-    sums = partial.cpu().double().sum(1)
+    sums = partial.cpu().double() / 2.0**20
     np.testing.assert_allclose(sums.numpy(), ref.sum((1, 2)).numpy(), rtol=1e-4, atol=1e-3)
+    # the squeeze is order independent: a second run gives the identical integers
+    again = torch.zeros_like(partial)
+    ops.depthwise_conv(x.to(DEV), out, wk.reshape(k * k, c).to(DEV),
+                       bias.to(DEV) if has_bias else None, act, k, s, again)
+    torch.cuda.synchronize()
+    assert torch.equal(again, partial)
 
 
 def test_se_fc():
   ops = _ops()
-  n, tiles, c, se, nout = 3, 7, 96, 4, 24
+  n, c, se, nout = 3, 96, 4, 24
   g = torch.Generator().manual_seed(5)
-  partial = torch.randn(n, tiles, c, generator=g)
+  sums = torch.randn(n, c, generator=g) * 20
+  se_sum = torch.round(sums.double() * 2.0**20).to(torch.int64)
+  nxt = torch.full((n, 144), 123, dtype=torch.int64, device=DEV)
   w1, b1 = torch.randn(se, c, generator=g) * 0.2, torch.randn(se, generator=g) * 0.1
   w2, b2 = torch.randn(c, se, generator=g) * 0.5, torch.randn(c, generator=g) * 0.1
   wt = torch.randn(nout, c, generator=g).half()
   gate = torch.empty(n, c, device=DEV)
   wt_scaled = torch.empty(n, nout, c, dtype=torch.float16, device=DEV)
   inv_hw = 1.0 / 50.0
-  ops.se_fc(partial.to(DEV), inv_hw, w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), gate,
-            utils.ACT_SWISH, wt.to(DEV), wt_scaled)
+  ops.se_fc(se_sum.to(DEV), inv_hw, w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), gate,
+            utils.ACT_SWISH, wt.to(DEV), wt_scaled, nxt)
   torch.cuda.synchronize()
-  mean = partial.double().sum(1) * inv_hw
+  assert int(nxt.abs().sum()) == 0          # the next block's accumulator was cleared
+  mean = se_sum.double() / 2.0**20 * inv_hw
   r = mean @ w1.double().T + b1.double()
   r = r * torch.sigmoid(r)
   ref_gate = torch.sigmoid(r @ w2.double().T + b2.double())
