@@ -28,6 +28,9 @@ SIGNATURES = {
     'edet_version': (c_int, []),
     'edet_last_error': (ctypes.c_char_p, []),
     'edet_device_info': (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    'edet_preprocess': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                ctypes.POINTER(c_float), ctypes.POINTER(c_float),
+                                ctypes.POINTER(c_float), c_void_p]),
     'edet_stem_conv': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                c_int, c_int, c_void_p]),
     'edet_pointwise_conv': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,

@@ -493,22 +493,32 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
     if (warp == (owner >> 5)) {
       const int begin = sm.begin[slot];
       const float4 cb = bx[i];
-      for (int j = begin + lane; j < nsel; j += 32) {
-        const float simv = iou_tf(cb, sm.sel_box[j]);
-        float wgt = static_cast<float>(exp(static_cast<double>(__fmul_rn(__fmul_rn(scale, simv), simv))));
-        if (!(soft || simv <= iou_thr)) wgt = 0.f;
-        sm.sim[j] = simv;
-        sm.wgt[j] = wgt;
-      }
-      __syncwarp();
-      if (tid == owner) {
-        float cur = s;
-        bool hard = false;
-        for (int j = nsel - 1; j >= begin; --j) {
-          cur = __fmul_rn(cur, sm.wgt[j]);
-          if (!soft && sm.sim[j] > iou_thr) { hard = true; break; }
-          if (cur <= score_thr) break;
+      // Newest -> oldest over the boxes selected since this candidate's last visit, 32 at a
+      // time.  A non-overlapping box has weight exp(0) == 1 exactly and cannot trigger either
+      // break, so only the overlapping ones are evaluated (fp64 exp) and applied, in order.
+      float cur = s;
+      bool hard = false, done = false;
+      for (int hi = nsel; hi > begin && !done; hi -= 32) {
+        const int j = hi - 1 - lane;                  // lane 0 = newest of this chunk
+        float simv = 0.f;
+        if (j >= begin) simv = iou_tf(cb, sm.sel_box[j]);
+        unsigned mask = __ballot_sync(0xffffffffu, simv > 0.f);
+        float wgt = 1.f;
+        if (simv > 0.f) {
+          wgt = static_cast<float>(exp(static_cast<double>(__fmul_rn(__fmul_rn(scale, simv), simv))));
+          if (!(soft || simv <= iou_thr)) wgt = 0.f;
         }
+        while (mask) {                                // ascending lane = descending j
+          const int l = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float wl = __shfl_sync(0xffffffffu, wgt, l);
+          const float sl = __shfl_sync(0xffffffffu, simv, l);
+          cur = __fmul_rn(cur, wl);
+          if (!soft && sl > iou_thr) { hard = true; done = true; break; }
+          if (cur <= score_thr) { done = true; break; }
+        }
+      }
+      if (tid == owner) {
         float new_s = -CUDART_INF_F;
         if (!hard) {
           if (cur == s) {

@@ -1,0 +1,188 @@
+"""`ServingDriver` on the B200 path: same call surface as the reference's
+/root/reference/efficientdet/inference.py:340-554.
+
+  driver = inference.ServingDriver('efficientdet-d0', ckpt_path, batch_size=len(imgs))
+  driver.build()
+  predictions = driver.serve_images(imgs)        # float32 [N, max_output_size, 7]
+                                                 # rows [image_id, ymin, xmin, ymax, xmax, score, class]
+
+Mirrored behaviour: constructor arguments and defaults (:389-427), `params` = registry config +
+`model_params` + `is_training_bn=False`, lazy `build()` on first serve (:493-494, :549-550),
+`build(params_override)` returning the {'image_files','image_arrays','prediction'} dict
+(:440-474), `serve_files` (decodes with PIL instead of tf.io.decode_image), `serve_images`,
+`benchmark` (1 warm run + 10 timed runs, prints the same two lines, :500-524).  Out of scope and
+raising NotImplementedError: `visualize`, `load`, `freeze`, `export` (SavedModel / TFLite /
+TensorRT — SURVEY.md section 2 row 8).
+
+`ckpt_path`: '_' (the reference's "don't load a checkpoint" sentinel, inference.py:218-220)
+gives seeded synthetic weights; a path to an .npz whose keys are the reference variable names
+(Keras layouts, see weights.py) loads real weights.
+
+The whole request runs on the device: H2D copy of the uint8 images -> edet_preprocess ->
+network -> pre-NMS -> NMS -> D2H copy of the [N, max_output_size, 7] detections.
+"""
+import copy
+import io
+import time
+
+import numpy as np
+import torch
+
+from automl_b200 import hparams_config
+from automl_b200 import ops
+from automl_b200 import weights as weights_lib
+from automl_b200.arch import DetArch
+from automl_b200.engine import Engine
+
+
+def load_weights(ckpt_path, arch, seed=0):
+  if ckpt_path == '_' or ckpt_path is None:
+    return weights_lib.synthetic_weights(arch, seed)
+  data = np.load(ckpt_path)
+  specs = weights_lib.variable_specs(arch)
+  missing = [k for k in specs if k not in data]
+  if missing:
+    raise ValueError('checkpoint %s lacks %d variables, e.g. %s' % (ckpt_path, len(missing), missing[:3]))
+  out = {}
+  for k, spec in specs.items():
+    v = np.asarray(data[k], np.float32)
+    if tuple(v.shape) != tuple(spec.shape):
+      raise ValueError('variable %s has shape %s, expected %s' % (k, v.shape, spec.shape))
+    out[k] = v
+  return out
+
+
+def image_preprocess(image, image_size, mean_rgb, stddev_rgb, device='cuda:0'):
+  """inference.py:37-56 for one uint8 HxWx3 image: (float32 [H,W,3] device tensor, scale)."""
+  from automl_b200 import utils
+  oh, ow = utils.parse_image_size(image_size)
+  raw = torch.as_tensor(np.ascontiguousarray(image), dtype=torch.uint8).to(device)[None]
+  out = torch.empty(1, oh, ow, 3, dtype=torch.float32, device=device)
+  scale = ops.preprocess(raw, out, _rgb3(mean_rgb), _rgb3(stddev_rgb))
+  return out[0], scale
+
+
+def _rgb3(v):
+  if isinstance(v, (int, float)):
+    return [float(v)] * 3
+  return [float(x) for x in v]
+
+
+class ServingDriver(object):
+  """A driver for serving single or batch images (reference inference.py:340)."""
+
+  def __init__(self, model_name, ckpt_path, batch_size=1, use_xla=False, min_score_thresh=None,
+               max_boxes_to_draw=None, line_thickness=None, model_params=None, device='cuda:0',
+               image_id_base=0):
+    self.model_name = model_name
+    self.ckpt_path = ckpt_path
+    self.batch_size = batch_size
+    self.params = hparams_config.get_detection_config(model_name).as_dict()
+    if model_params:
+      self.params.update(model_params)
+    self.params.update(dict(is_training_bn=False))
+    self.label_map = self.params.get('label_map', None)
+    self.signitures = None   # (sic) the reference's spelling
+    self.engine = None
+    self.use_xla = use_xla    # accepted for signature compatibility; there is no XLA here
+    self.min_score_thresh = min_score_thresh
+    self.max_boxes_to_draw = max_boxes_to_draw
+    self.line_thickness = line_thickness
+    self.device = device
+    self.image_id_base = image_id_base
+    self._raw_shape = None
+
+  # ---- build ---------------------------------------------------------------------------------
+  def build(self, params_override=None):
+    """Builds the engine (weights, buffers, launch list) and returns the signature dict."""
+    params = copy.deepcopy(self.params)
+    if params_override:
+      params.update(params_override)
+    if not self.batch_size:
+      raise NotImplementedError('dynamic batch size: pass the serving batch_size explicitly')
+    config = hparams_config.Config(params)
+    arch = DetArch(config)
+    weights = load_weights(self.ckpt_path, arch)
+    self.config = config
+    self.engine = Engine(config, weights, self.batch_size, device=self.device,
+                         image_id_base=self.image_id_base)
+    self.mean_rgb = _rgb3(params['mean_rgb'])
+    self.stddev_rgb = _rgb3(params['stddev_rgb'])
+    self._host_det = torch.empty(self.batch_size, self.engine.max_output_size, 7).pin_memory()
+    self._scales = torch.empty(self.batch_size, dtype=torch.float32).pin_memory()
+    self.signitures = {
+        'image_files': 'image_files',     # bytes of encoded images (serve_files)
+        'image_arrays': 'image_arrays',   # uint8 HxWx3 arrays (serve_images)
+        'prediction': self.engine.detections,
+    }
+    return self.signitures
+
+  # ---- serving -------------------------------------------------------------------------------
+  def _stage_raw(self, image_arrays):
+    """Uploads the uint8 images and runs the device pre-process into the engine input."""
+    eng = self.engine
+    if len(image_arrays) != self.batch_size:
+      raise ValueError('expected %d images, got %d' % (self.batch_size, len(image_arrays)))
+    if isinstance(image_arrays, torch.Tensor):   # [N,h,w,3] uint8 (e.g. pinned host memory)
+      shapes = {tuple(image_arrays.shape[1:])}
+    else:
+      shapes = {tuple(np.shape(im)) for im in image_arrays}
+    if len(shapes) == 1:
+      if isinstance(image_arrays, torch.Tensor):
+        batch = image_arrays
+      else:
+        batch = torch.as_tensor(np.ascontiguousarray(np.stack(image_arrays)), dtype=torch.uint8)
+      raw = batch.to(self.device, non_blocking=True)
+      scale = ops.preprocess(raw, eng.input, self.mean_rgb, self.stddev_rgb)
+      self._scales.fill_(scale)
+    else:  # ragged batch: one pre-process launch per image (like the reference's python loop)
+      for i, im in enumerate(image_arrays):
+        raw = torch.as_tensor(np.ascontiguousarray(im), dtype=torch.uint8).to(self.device)[None]
+        self._scales[i] = ops.preprocess(raw, eng.input[i:i + 1], self.mean_rgb, self.stddev_rgb)
+    eng.image_scales.copy_(self._scales, non_blocking=True)
+
+  def serve_images(self, image_arrays):
+    """image_arrays: list (or array) of HxWx3 uint8 images -> float32 [N, max_output_size, 7]."""
+    if self.engine is None:
+      self.build()
+    with torch.cuda.device(self.device):
+      self._stage_raw(image_arrays)
+      self.engine.run(postprocess=True)
+      self._host_det.copy_(self.engine.detections, non_blocking=True)
+      torch.cuda.current_stream().synchronize()
+    return self._host_det.numpy().copy()
+
+  def serve_files(self, image_files):
+    """image_files: list of encoded image bytes (jpeg/png)."""
+    from PIL import Image  # pylint: disable=g-import-not-at-top
+    arrays = [np.asarray(Image.open(io.BytesIO(b)).convert('RGB')) for b in image_files]
+    return self.serve_images(arrays)
+
+  def benchmark(self, image_arrays, trace_filename=None):
+    """1 warm-up run then the mean of 10 runs, printed like the reference (:500-524)."""
+    if self.engine is None:
+      self.build()
+    self.serve_images(image_arrays)
+    start = time.perf_counter()
+    for _ in range(10):
+      self.serve_images(image_arrays)
+    end = time.perf_counter()
+    inference_time = (end - start) / 10
+    print('Per batch inference time: ', inference_time)
+    print('FPS: ', self.batch_size / inference_time)
+    if trace_filename:
+      raise NotImplementedError('chrome traces are replaced by ncu / CUDA events (see bench.py)')
+    return inference_time
+
+  # ---- out of scope ----------------------------------------------------------------------------
+  def visualize(self, image, prediction, **kwargs):
+    raise NotImplementedError('visualisation is out of scope (SURVEY.md section 2 row 18)')
+
+  def load(self, saved_model_dir_or_frozen_graph):
+    raise NotImplementedError('SavedModel / frozen-graph loading is out of scope')
+
+  def freeze(self):
+    raise NotImplementedError('graph freezing is out of scope')
+
+  def export(self, *args, **kwargs):
+    raise NotImplementedError('SavedModel / TFLite / TensorRT export is out of scope')

@@ -28,6 +28,18 @@ def _ptr(t, dtype=None):
   return ctypes.c_void_p(t.data_ptr())
 
 
+def preprocess(raw, out, mean_rgb, stddev_rgb):
+  """raw uint8 [N,h,w,3] -> out fp32 [N,H,W,3]; returns image_scale_to_original (float)."""
+  n, h, w, _ = raw.shape
+  _, oh, ow, _ = out.shape
+  mean = (ctypes.c_float * 3)(*[float(v) for v in mean_rgb])
+  std = (ctypes.c_float * 3)(*[float(v) for v in stddev_rgb])
+  scale = ctypes.c_float(0.0)
+  _lib.call('edet_preprocess', _ptr(raw, torch.uint8), _ptr(out, torch.float32), n, h, w, oh, ow,
+            mean, std, ctypes.byref(scale), _stream())
+  return scale.value
+
+
 def stem_conv(images, out, w, bias, act):
   """images fp32 [N,H,W,3] -> out fp16 [N,ceil(H/2),ceil(W/2),C]."""
   n, h, wd, c3 = images.shape

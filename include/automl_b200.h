@@ -60,6 +60,19 @@ const char* edet_last_error(void);
 int edet_device_info(int* sm_count, int* cc);
 
 /*
+ * Serving pre-process: uint8 HWC images (all the same size) -> normalise -> aspect-preserving
+ * bilinear resize (TF2 half-pixel centres) -> zero pad to [out_h, out_w].
+ * Replaces inference.image_preprocess inference.py:37-56 and
+ * dataloader.DetectionInputProcessor dataloader.py:59-65, 115-142.
+ *   in  uint8 [n, h, w, 3]     out float32 [n, out_h, out_w, 3]
+ *   h_mean_rgb / h_stddev_rgb: HOST float32[3];  h_image_scale: HOST out, scale back to the
+ *   original image (image_scale_to_original), may be NULL
+ */
+int edet_preprocess(const uint8_t* in, float* out, int n, int h, int w, int out_h, int out_w,
+                    const float* h_mean_rgb, const float* h_stddev_rgb, float* h_image_scale,
+                    edet_stream_t stream);
+
+/*
  * Stem: Conv2D 3x3 stride 2 'same' (3 -> cout, no bias) + BN + act.
  * Replaces backbone/efficientnet_model.py:511-527 (Stem.call).
  *   in   float32 [n, h, w, 3] NHWC            out  half [n, ceil(h/2), ceil(w/2), cout]
