@@ -270,46 +270,88 @@ nms_v5_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
 
 
 // ------------------------------------------------------------------------------------------
-// Fast path: the same algorithm on the top candidates only, entirely in shared memory.
+// Fast path: the same algorithm, batched, on the top candidates only, in shared memory.
 //
-// Only the highest-scoring candidates are ever popped before max_output_size boxes are selected
-// (a few hundred for a 76 725-anchor image), so each image first compacts its top <= kFastCap
-// candidates into shared memory (adaptive two-level histogram threshold on the score bits; the
-// boxes stay in global memory and are fetched when a candidate is popped), then runs the
-// exact lazy-suppression loop there.  Exactness is PROVEN per image at run time: every popped
-// (stale) score must be strictly greater than the best excluded score; otherwise the image is
-// flagged and the full-queue kernel above recomputes it.
+// TF's NMS-V5 pops one candidate at a time from a lazily-updated max-heap.  Between two
+// selections the selected set S is fixed, so the pops of that "period" can be replayed in
+// parallel without changing a single bit:
+//   * walk the queue in descending stale-score order; every visited candidate x gets its
+//     pending suppression applied (boxes begin_x..|S|-1, newest first, with TF's break rules),
+//     giving u_x -- independent of the other candidates, so a whole chunk is done at once
+//     (8 lanes per candidate, 64 candidates per chunk);
+//   * the period ends at the first position p where either a candidate updated earlier in the
+//     period ("fresh", already up to date) now beats x_p -- then that fresh candidate is
+//     selected with its decayed score -- or x_p itself came out unchanged -- then x_p is
+//     selected.  Everything before p is committed (re-queued with its new score, or dropped).
+// The queue is (A) the compacted top candidates, sorted once by (score desc, index asc), consumed
+// through a pointer, plus (B) a small sorted array of re-queued candidates; a chunk is the
+// rank-merge of the heads of A and B.
+//
+// Only the top <= kBCapA candidates per image are considered (adaptive two-level histogram
+// threshold on the score bits); exactness is PROVEN per image at run time -- every candidate
+// touched must score strictly above the best excluded one -- otherwise the image is flagged and
+// the full-queue kernel above recomputes it.
 // ------------------------------------------------------------------------------------------
-constexpr int kFastThreads = 512;
-constexpr int kFastCap = 16384;
-constexpr int kFastPer = kFastCap / kFastThreads;  // 32 slots per thread
+constexpr int kBT = 512;            // threads per image
+constexpr int kBCapA = 8192;
+constexpr int kBCapB = 4096;
+constexpr int kBChunk = 64;         // candidates per chunk (8 lanes each)
 constexpr int kFastBins = 2048;
-constexpr int kFastWarps = kFastThreads / 32;
 
 __device__ __forceinline__ uint32_t score_key(float s) {
   const uint32_t b = __float_as_uint(s);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // monotone float -> uint
 }
+__device__ __forceinline__ float key_score(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+// 64-bit queue key: larger == popped earlier (score descending, then index ascending)
+__device__ __forceinline__ unsigned long long make_qkey(float s, int idx) {
+  return (static_cast<unsigned long long>(score_key(s)) << 32) |
+         static_cast<unsigned long long>(~static_cast<uint32_t>(idx));
+}
+__device__ __forceinline__ float qkey_score(unsigned long long k) {
+  return key_score(static_cast<uint32_t>(k >> 32));
+}
+__device__ __forceinline__ int qkey_idx(unsigned long long k) {
+  return static_cast<int>(~static_cast<uint32_t>(k));
+}
 
-struct FastSmem {
-  float score[kFastCap];
-  int idx[kFastCap];
-  unsigned short begin[kFastCap];
+struct BatchSmem {
+  unsigned long long a_key[kBCapA];   // sorted descending; consumed through `ptr`
+  unsigned long long b_key[kBCapB];   // sorted descending
+  unsigned short b_begin[kBCapB];
   int hist[kFastBins];
   float4 sel_box[kNmsMaxOut];
   int sel_idx[kNmsMaxOut];
   float sel_score[kNmsMaxOut];
-  float sim[kNmsMaxOut];
-  float wgt[kNmsMaxOut];
-  float red_s[kFastWarps];
-  int red_i[kFastWarps];
-  int red_slot[kFastWarps];
+  unsigned long long c_key[kBChunk];    // stale key of the chunk position
+  unsigned long long c_fresh[kBChunk];  // key after the update (0: dropped / not re-queued)
+  float c_u[kBChunk];
+  unsigned short c_begin[kBChunk];
+  short c_src[kBChunk];                 // >= 0: offset in A from ptr; < 0: -(B index) - 1
+  unsigned char c_unchanged[kBChunk];
+  unsigned long long n_key[kBChunk];    // re-queued entries of this commit, sorted descending
+  float red_s[kBT / 32];
   uint32_t kmin, kmax;
-  int count, nsel, bstar, sstar, fail;
+  int count, bstar, sstar, fail;
+  int ptr, nb, m, chunk_n;
+  int stop_p, sel_pos, sel_is_fresh, pa, pb, n_new;
   float excl_max;
 };
 
-__global__ void __launch_bounds__(kFastThreads)
+// number of elements of the descending array arr[0..n) that are greater than key
+__device__ __forceinline__ int count_greater(const unsigned long long* arr, int n,
+                                             unsigned long long key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (arr[mid] > key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kBT)
 nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
                    const int32_t* __restrict__ classes, const float* __restrict__ image_scales,
                    int image_id_base, int k, int max_out, float iou_thr, float score_thr,
@@ -317,7 +359,7 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
                    int32_t* __restrict__ sel_index, int32_t* __restrict__ valid,
                    int32_t* __restrict__ need_full) {
   extern __shared__ __align__(16) uint8_t fast_raw[];
-  FastSmem& sm = *reinterpret_cast<FastSmem*>(fast_raw);
+  BatchSmem& sm = *reinterpret_cast<BatchSmem*>(fast_raw);
   const int n = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float4* bx = reinterpret_cast<const float4*>(boxes) + static_cast<size_t>(n) * k;
@@ -327,7 +369,7 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
 
   // ---- A. key range of the valid candidates ----
   uint32_t kmin = 0xffffffffu, kmax = 0u;
-  for (int i = tid; i < k; i += kFastThreads) {
+  for (int i = tid; i < k; i += kBT) {
     const float s = sc[i];
     if (s > score_thr) {
       const uint32_t key = score_key(s);
@@ -336,10 +378,11 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
     }
   }
   if (tid == 0) {
-    sm.kmin = 0xffffffffu; sm.kmax = 0u; sm.count = 0; sm.nsel = 0; sm.fail = 0;
+    sm.kmin = 0xffffffffu; sm.kmax = 0u; sm.count = 0; sm.fail = 0;
     sm.excl_max = -CUDART_INF_F; sm.bstar = 0; sm.sstar = 0;
+    sm.ptr = 0; sm.nb = 0; sm.m = 0;
   }
-  for (int i = tid; i < kFastBins; i += kFastThreads) sm.hist[i] = 0;
+  for (int i = tid; i < kFastBins; i += kBT) sm.hist[i] = 0;
   __syncthreads();
   atomicMin(&sm.kmin, kmin);
   atomicMax(&sm.kmax, kmax);
@@ -360,7 +403,7 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
   };
   // ---- B. coarse histogram -> threshold bin ----
   if (any_valid) {
-    for (int i = tid; i < k; i += kFastThreads) {
+    for (int i = tid; i < k; i += kBT) {
       const float s = sc[i];
       int sub;
       if (s > score_thr) atomicAdd(&sm.hist[bin_of(score_key(s), sub)], 1);
@@ -369,7 +412,7 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
   __syncthreads();
   if (tid == 0) {
     int acc = 0, b = kFastBins;
-    while (b > 0 && acc + sm.hist[b - 1] <= kFastCap) acc += sm.hist[--b];
+    while (b > 0 && acc + sm.hist[b - 1] <= kBCapA) acc += sm.hist[--b];
     sm.bstar = b;       // bins >= bstar are taken whole; bin bstar-1 is refined below
     sm.count = acc;     // (reused as the running total for the refinement)
   }
@@ -378,10 +421,10 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
   const int coarse_total = sm.count;
   __syncthreads();
   // ---- B2. refine the boundary bin with a second-level histogram ----
-  for (int i = tid; i < kFastBins; i += kFastThreads) sm.hist[i] = 0;
+  for (int i = tid; i < kFastBins; i += kBT) sm.hist[i] = 0;
   __syncthreads();
   if (any_valid && bstar > 0) {
-    for (int i = tid; i < k; i += kFastThreads) {
+    for (int i = tid; i < k; i += kBT) {
       const float s = sc[i];
       if (s > score_thr) {
         int sub;
@@ -393,7 +436,7 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
   if (tid == 0) {
     int acc = coarse_total, sb = kFastBins;
     if (bstar > 0)
-      while (sb > 0 && acc + sm.hist[sb - 1] <= kFastCap) acc += sm.hist[--sb];
+      while (sb > 0 && acc + sm.hist[sb - 1] <= kBCapA) acc += sm.hist[--sb];
     sm.sstar = sb;
     sm.count = 0;
     if (any_valid && acc == 0) sm.fail = 1;  // one score value alone overflows the capacity
@@ -403,16 +446,14 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
   // ---- D. compaction into shared memory; best excluded score ----
   float excl = -CUDART_INF_F;
   if (any_valid && !sm.fail) {
-    for (int i = tid; i < k; i += kFastThreads) {
+    for (int i = tid; i < k; i += kBT) {
       const float s = sc[i];
       if (s > score_thr) {
         int sub;
         const int b = bin_of(score_key(s), sub);
         if (b >= bstar || (b == bstar - 1 && sub >= sstar)) {
           const int slot = atomicAdd(&sm.count, 1);
-          sm.score[slot] = s;
-          sm.idx[slot] = i;
-          sm.begin[slot] = 0;
+          sm.a_key[slot] = make_qkey(s, i);
         } else {
           excl = fmaxf(excl, s);
         }
@@ -425,127 +466,240 @@ nms_v5_fast_kernel(const float* __restrict__ boxes, const float* __restrict__ sc
   __syncthreads();
   if (tid == 0) {
     float e = -CUDART_INF_F;
-    for (int w = 0; w < kFastWarps; ++w) e = fmaxf(e, sm.red_s[w]);
+    for (int w = 0; w < kBT / 32; ++w) e = fmaxf(e, sm.red_s[w]);
     sm.excl_max = e;
   }
-  __syncthreads();
   const int count = sm.count;
-  const float excl_max = sm.excl_max;
-  for (int sl = count + tid; sl < kFastCap; sl += kFastThreads) sm.score[sl] = -CUDART_INF_F;
+  int npow2 = 1;
+  while (npow2 < count) npow2 <<= 1;
+  for (int sl = count + tid; sl < npow2; sl += kBT) sm.a_key[sl] = 0ull;
   __syncthreads();
-
-  // thread-local best over its interleaved slots (slot = tid + u * kFastThreads)
-  float my_s = -CUDART_INF_F;
-  int my_i = 0x7fffffff, my_slot = -1;
-  auto rescan = [&]() {
-    my_s = -CUDART_INF_F; my_i = 0x7fffffff; my_slot = -1;
-#pragma unroll 8
-    for (int u = 0; u < kFastPer; ++u) {
-      const int sl = tid + u * kFastThreads;
-      const float v = sm.score[sl];
-      if (v > -CUDART_INF_F) {
-        const int id = sm.idx[sl];
-        if (better(v, id, my_s, my_i)) { my_s = v; my_i = id; my_slot = sl; }
+  const float excl_max = sm.excl_max;
+  // ---- sort A descending (bitonic, in shared memory) ----
+  for (int size = 2; size <= npow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (npow2 >> 1); t += kBT) {
+        const int lo = 2 * t - (t & (stride - 1));   // index with bit `stride` cleared
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long x = sm.a_key[lo], y = sm.a_key[hi];
+        if ((x < y) == desc) { sm.a_key[lo] = y; sm.a_key[hi] = x; }
       }
+      __syncthreads();
     }
-  };
-  rescan();
+  }
 
-  // ---- E. exact lazy-suppression loop ----
+  // ---- E. periods ----
+  const int cand = tid >> 3, sub = tid & 7;          // 8 lanes per chunk candidate
+  const unsigned gmask = 0xffu << ((lane >> 3) << 3);  // this candidate's lanes in the warp
   while (!sm.fail) {
-    const int nsel = sm.nsel;   // stable here: only written between the two barriers below
-    float s = my_s;
-    int i = my_i, slot = my_slot;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float so = __shfl_xor_sync(0xffffffffu, s, o);
-      const int io = __shfl_xor_sync(0xffffffffu, i, o);
-      const int lo = __shfl_xor_sync(0xffffffffu, slot, o);
-      if (better(so, io, s, i)) { s = so; i = io; slot = lo; }
-    }
-    if (lane == 0) { sm.red_s[warp] = s; sm.red_i[warp] = i; sm.red_slot[warp] = slot; }
-    __syncthreads();
-    // every warp reduces the per-warp partials itself: no second barrier for the broadcast
-    s = lane < kFastWarps ? sm.red_s[lane] : -CUDART_INF_F;
-    i = lane < kFastWarps ? sm.red_i[lane] : 0x7fffffff;
-    slot = lane < kFastWarps ? sm.red_slot[lane] : -1;
-#pragma unroll
-    for (int o = kFastWarps / 2; o > 0; o >>= 1) {
-      const float so = __shfl_xor_sync(0xffffffffu, s, o);
-      const int io = __shfl_xor_sync(0xffffffffu, i, o);
-      const int lo = __shfl_xor_sync(0xffffffffu, slot, o);
-      if (better(so, io, s, i)) { s = so; i = io; slot = lo; }
-    }
-    s = __shfl_sync(0xffffffffu, s, 0);
-    i = __shfl_sync(0xffffffffu, i, 0);
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    if (nsel >= max_out) break;
-    if (s == -CUDART_INF_F) {           // queue exhausted
+    const int m = sm.m, ptr = sm.ptr, nb = sm.nb;     // stable: written only before the last barrier
+    if (m >= max_out) break;
+    const int ka = min(kBChunk, count - ptr), kb = min(kBChunk, nb);
+    if (ka + kb == 0) {                               // queue exhausted
       if (excl_max > -CUDART_INF_F) { if (tid == 0) sm.fail = 2; __syncthreads(); }
       break;
     }
-    if (!(s > excl_max)) {              // an excluded candidate could be next: not provable
-      if (tid == 0) sm.fail = 3;
-      __syncthreads();
-      break;
+    // -- chunk = rank-merge of the heads of A and B --
+    if (tid < ka) {
+      const unsigned long long key = sm.a_key[ptr + tid];
+      const int r = tid + count_greater(sm.b_key, kb, key);
+      if (r < kBChunk) {
+        sm.c_key[r] = key; sm.c_begin[r] = 0; sm.c_src[r] = static_cast<short>(tid);
+      }
+    } else if (tid >= kBChunk && tid < kBChunk + kb) {
+      const int j = tid - kBChunk;
+      const unsigned long long key = sm.b_key[j];
+      const int r = j + count_greater(sm.a_key + ptr, ka, key);
+      if (r < kBChunk) {
+        sm.c_key[r] = key; sm.c_begin[r] = sm.b_begin[j]; sm.c_src[r] = static_cast<short>(-j - 1);
+      }
     }
-    const int owner = slot % kFastThreads;
-    if (warp == (owner >> 5)) {
-      const int begin = sm.begin[slot];
-      const float4 cb = bx[i];
-      // Newest -> oldest over the boxes selected since this candidate's last visit, 32 at a
-      // time.  A non-overlapping box has weight exp(0) == 1 exactly and cannot trigger either
-      // break, so only the overlapping ones are evaluated (fp64 exp) and applied, in order.
+    const int chunk_n = min(kBChunk, ka + kb);
+    __syncthreads();
+    // -- pending suppression of every chunk candidate, 8 lanes each --
+    if (cand < chunk_n) {
+      const unsigned long long key = sm.c_key[cand];
+      const float s = qkey_score(key);
+      const int idx = qkey_idx(key);
+      const int begin = sm.c_begin[cand];
+      const float4 cb = bx[idx];
       float cur = s;
       bool hard = false, done = false;
-      for (int hi = nsel; hi > begin && !done; hi -= 32) {
-        const int j = hi - 1 - lane;                  // lane 0 = newest of this chunk
+      for (int hi = m; hi > begin && !done; hi -= 8) {
+        const int j = hi - 1 - sub;                    // sub-lane 0 = newest of this group of 8
         float simv = 0.f;
         if (j >= begin) simv = iou_tf(cb, sm.sel_box[j]);
-        unsigned mask = __ballot_sync(0xffffffffu, simv > 0.f);
+        unsigned mask = (__ballot_sync(gmask, simv > 0.f) >> ((lane >> 3) << 3)) & 0xffu;
         float wgt = 1.f;
         if (simv > 0.f) {
           wgt = static_cast<float>(exp(static_cast<double>(__fmul_rn(__fmul_rn(scale, simv), simv))));
           if (!(soft || simv <= iou_thr)) wgt = 0.f;
         }
-        while (mask) {                                // ascending lane = descending j
+        while (mask) {                                 // ascending sub-lane = descending j
           const int l = __ffs(mask) - 1;
           mask &= mask - 1;
-          const float wl = __shfl_sync(0xffffffffu, wgt, l);
-          const float sl = __shfl_sync(0xffffffffu, simv, l);
+          const int src = (lane & ~7) + l;
+          const float wl = __shfl_sync(gmask, wgt, src);
+          const float sl = __shfl_sync(gmask, simv, src);
           cur = __fmul_rn(cur, wl);
           if (!soft && sl > iou_thr) { hard = true; done = true; break; }
           if (cur <= score_thr) { done = true; break; }
         }
       }
-      if (tid == owner) {
-        float new_s = -CUDART_INF_F;
-        if (!hard) {
-          if (cur == s) {
-            sm.sel_box[nsel] = cb;
-            sm.sel_idx[nsel] = i;
-            sm.sel_score[nsel] = cur;
-            sm.nsel = nsel + 1;
-          } else if (cur > score_thr) {
-            new_s = cur;
-            sm.begin[slot] = static_cast<unsigned short>(nsel);
-          }
+      if (sub == 0) {
+        const bool unchanged = !hard && (cur == s);
+        const bool requeue = !hard && !unchanged && (cur > score_thr);
+        sm.c_u[cand] = cur;
+        sm.c_unchanged[cand] = unchanged ? 1 : 0;
+        sm.c_fresh[cand] = requeue ? make_qkey(cur, idx) : 0ull;
+      }
+    }
+    __syncthreads();
+    // -- where does the period end? (warp 0; two chunk positions per lane) --
+    if (warp == 0) {
+      unsigned long long f0 = lane < chunk_n ? sm.c_fresh[lane] : 0ull;
+      unsigned long long f1 = lane + 32 < chunk_n ? sm.c_fresh[lane + 32] : 0ull;
+      // inclusive prefix max over 32 lanes, then shift to exclusive
+      unsigned long long p0 = f0, p1 = f1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t0 = __shfl_up_sync(0xffffffffu, p0, o);
+        const unsigned long long t1 = __shfl_up_sync(0xffffffffu, p1, o);
+        if (lane >= o) { p0 = max(p0, t0); p1 = max(p1, t1); }
+      }
+      const unsigned long long tot0 = __shfl_sync(0xffffffffu, p0, 31);
+      unsigned long long e0 = __shfl_up_sync(0xffffffffu, p0, 1);
+      unsigned long long e1 = __shfl_up_sync(0xffffffffu, p1, 1);
+      if (lane == 0) { e0 = 0ull; e1 = 0ull; }
+      e1 = max(e1, tot0);
+      const bool in0 = lane < chunk_n, in1 = lane + 32 < chunk_n;
+      const bool stop0 = in0 && ((e0 > sm.c_key[lane]) || sm.c_unchanged[lane]);
+      const bool stop1 = in1 && ((e1 > sm.c_key[lane + 32]) || sm.c_unchanged[lane + 32]);
+      const unsigned b0 = __ballot_sync(0xffffffffu, stop0), b1 = __ballot_sync(0xffffffffu, stop1);
+      int p = chunk_n;
+      if (b0) p = __ffs(b0) - 1; else if (b1) p = 32 + __ffs(b1) - 1;
+      const bool stopped = p < chunk_n;
+      // the exclusive prefix max at p decides between the two endings
+      unsigned long long ep = 0ull;
+      if (stopped) ep = p < 32 ? __shfl_sync(0xffffffffu, e0, p) : __shfl_sync(0xffffffffu, e1, p - 32);
+      const bool fresh_wins = stopped && ep > sm.c_key[stopped ? p : 0];
+      // position of the fresh candidate that holds the prefix max
+      const unsigned m0 = __ballot_sync(0xffffffffu, fresh_wins && f0 == ep && lane < p);
+      const unsigned m1 = __ballot_sync(0xffffffffu, fresh_wins && f1 == ep && lane + 32 < p);
+      int sel_pos = -1;
+      if (stopped) sel_pos = fresh_wins ? (m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1) : p;
+      // elements consumed from the queue: positions < pe (the selected x_p is consumed too)
+      const int pe = stopped ? (fresh_wins ? p : p + 1) : chunk_n;
+      const bool c0 = lane < pe, c1 = lane + 32 < pe;
+      const int a0 = c0 && sm.c_src[lane] >= 0, a1 = c1 && sm.c_src[lane + 32] >= 0;
+      const int pa = __popc(__ballot_sync(0xffffffffu, a0)) + __popc(__ballot_sync(0xffffffffu, a1));
+      const int pbv = __popc(__ballot_sync(0xffffffffu, c0 && !a0)) + __popc(__ballot_sync(0xffffffffu, c1 && !a1));
+      // re-queued entries: consumed, still alive, not the one being selected
+      const bool q0 = c0 && f0 != 0ull && lane != sel_pos;
+      const bool q1 = c1 && f1 != 0ull && lane + 32 != sel_pos;
+      const unsigned qb0 = __ballot_sync(0xffffffffu, q0), qb1 = __ballot_sync(0xffffffffu, q1);
+      const int n_new = __popc(qb0) + __popc(qb1);
+      // every element looked at must provably precede all excluded candidates
+      const int last = stopped ? p : chunk_n - 1;
+      if (lane == 0) {
+        if (!(qkey_score(sm.c_key[last]) > excl_max)) sm.fail = 3;
+        sm.stop_p = p; sm.sel_pos = sel_pos; sm.sel_is_fresh = fresh_wins ? 1 : 0;
+        sm.pa = pa; sm.pb = pbv; sm.n_new = n_new; sm.chunk_n = chunk_n;
+      }
+      // sorted list of the re-queued keys (rank by counting; keys are unique)
+      if (q0) {
+        int r = 0;
+        for (int t = 0; t < pe; ++t) {
+          const unsigned long long o = sm.c_fresh[t];
+          if (t != sel_pos && o > f0) ++r;
         }
-        sm.score[slot] = new_s;
-        rescan();
+        sm.n_key[r] = f0;
+      }
+      if (q1) {
+        int r = 0;
+        for (int t = 0; t < pe; ++t) {
+          const unsigned long long o = sm.c_fresh[t];
+          if (t != sel_pos && o > f1) ++r;
+        }
+        sm.n_key[r] = f1;
+      }
+    }
+    __syncthreads();
+    if (sm.fail) break;
+    // -- commit: B <- merge(B[pb..), re-queued), A pointer, selection --
+    {
+      const int pb = sm.pb, n_new = sm.n_new, sel_pos = sm.sel_pos;
+      const int nb_keep = nb - pb;
+      if (nb_keep + n_new > kBCapB) {
+        if (tid == 0) sm.fail = 4;
+        __syncthreads();
+        break;
+      }
+      // read phase (old B), positions computed by binary search in the other list
+      unsigned long long keep_key[kBCapB / kBT];
+      unsigned short keep_begin[kBCapB / kBT];
+      int keep_pos[kBCapB / kBT];
+#pragma unroll
+      for (int u = 0; u < kBCapB / kBT; ++u) {
+        const int i = pb + tid + u * kBT;
+        keep_pos[u] = -1;
+        if (i < nb) {
+          keep_key[u] = sm.b_key[i];
+          keep_begin[u] = sm.b_begin[i];
+          keep_pos[u] = (i - pb) + count_greater(sm.n_key, n_new, keep_key[u]);
+        }
+      }
+      int new_pos = -1;
+      unsigned long long new_key = 0ull;
+      if (tid < n_new) {
+        new_key = sm.n_key[tid];
+        new_pos = tid + count_greater(sm.b_key + pb, nb_keep, new_key);
+      }
+      float4 sbox = make_float4(0.f, 0.f, 0.f, 0.f);
+      int sidx = 0;
+      float sscore = 0.f;
+      if (tid == 0 && sel_pos >= 0) {
+        const unsigned long long key = sm.c_key[sel_pos];
+        sidx = qkey_idx(key);
+        sscore = sm.sel_is_fresh ? sm.c_u[sel_pos] : qkey_score(key);
+        sbox = bx[sidx];
+      }
+      __syncthreads();
+      // write phase
+#pragma unroll
+      for (int u = 0; u < kBCapB / kBT; ++u) {
+        if (keep_pos[u] >= 0) {
+          sm.b_key[keep_pos[u]] = keep_key[u];
+          sm.b_begin[keep_pos[u]] = keep_begin[u];
+        }
+      }
+      if (new_pos >= 0) {
+        sm.b_key[new_pos] = new_key;
+        sm.b_begin[new_pos] = static_cast<unsigned short>(m);   // up to date with all m boxes
+      }
+      if (tid == 0) {
+        sm.nb = nb_keep + n_new;
+        sm.ptr = ptr + sm.pa;
+        if (sel_pos >= 0) {
+          sm.sel_box[m] = sbox;
+          sm.sel_idx[m] = sidx;
+          sm.sel_score[m] = sscore;
+          sm.m = m + 1;
+        }
       }
     }
     __syncthreads();
   }
   __syncthreads();
   if (sm.fail) {
-    if (tid == 0) need_full[n] = sm.fail;   // reason code (1: tie overflow, 2: exhausted, 3: bound)
+    if (tid == 0) need_full[n] = sm.fail;  // reason (1 ties, 2 exhausted, 3 bound, 4 B overflow)
     return;
   }
   if (tid == 0) need_full[n] = 0;
-  const int nsel = sm.nsel;
+  const int nsel = sm.m;
   const float scale_img = image_scales ? image_scales[n] : 1.f;
-  for (int r = tid; r < max_out; r += kFastThreads) {
+  for (int r = tid; r < max_out; r += kBT) {
     const int idx = r < nsel ? sm.sel_idx[r] : 0;
     const float score = r < nsel ? sm.sel_score[r] : 0.f;
     const float4 b = bx[idx];
@@ -625,11 +779,11 @@ extern "C" int edet_nms_v5(const float* boxes, const float* scores, const int32_
   if (!configured) {
     EDET_CHECK_CUDA(cudaFuncSetAttribute(nms_v5_fast_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(FastSmem))));
+                                         static_cast<int>(sizeof(BatchSmem))));
     configured = true;
   }
   // fast path (top candidates in shared memory, exactness proven per image) ...
-  nms_v5_fast_kernel<<<n, kFastThreads, sizeof(FastSmem), as_stream(stream)>>>(
+  nms_v5_fast_kernel<<<n, kBT, sizeof(BatchSmem), as_stream(stream)>>>(
       boxes, scores, classes, image_scales, image_id_base, k, max_output_size, iou_threshold,
       score_threshold, soft_nms_sigma, clip_h, clip_w, detections, sel_index, valid, need_full);
   EDET_CHECK_LAUNCH();

@@ -295,6 +295,9 @@ def test_nms_v5_bit_exact(method, k):
              score_t, tf_sigma, (512.0, 512.0), det, sel, valid, work)
   torch.cuda.synchronize()
   det, sel, valid = det.cpu().numpy(), sel.cpu().numpy(), valid.cpu().numpy()
+  flags = work[-4 * n:].view(torch.int32).cpu().numpy()
+  if method == 'gaussian':
+    assert (flags == 0).all(), flags      # the batched shared-memory path proved itself exact
   for i in range(n):
     idx, sc, v = po.non_max_suppression_v5(boxes[i], scores[i], 100, iou_t, score_t, tf_sigma, True)
     assert valid[i] == v
