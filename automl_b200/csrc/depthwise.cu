@@ -65,33 +65,58 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
                          static_cast<size_t>(n) * h * wd * cp_count + cp;
     const int iy0 = oy0 * S - pad_t;
     const int ix0 = ox0 * S - pad_l;
-    unsigned col_ok = 0;
-#pragma unroll
-    for (int j = 0; j < IN_COLS; ++j)
-      if (ix0 + j >= 0 && ix0 + j < wd) col_ok |= 1u << j;
+    // Interior tiles (the vast majority) need no bounds predicate on any of their loads/stores.
+    const bool interior = iy0 >= 0 && iy0 + IN_ROWS <= h && ix0 >= 0 && ix0 + IN_COLS <= wd &&
+                          oy0 + ROWS <= ho && ox0 + TW <= wo;
+    const int row_stride = wd * cp_count;
+    const __half2* rowp = in2 + (iy0 * wd + ix0) * cp_count;   // may point outside; guarded below
 
+    if (interior) {
 #pragma unroll
-    for (int ir = 0; ir < IN_ROWS; ++ir) {
-      const int iy = iy0 + ir;
-      const bool row_ok = (iy >= 0) && (iy < h);
-      const __half2* rowp = in2 + (iy * wd + ix0) * cp_count;   // 32-bit offset within the image
-      float2 xv[IN_COLS];
+      for (int ir = 0; ir < IN_ROWS; ++ir) {
+        float2 xv[IN_COLS];
 #pragma unroll
-      for (int j = 0; j < IN_COLS; ++j) {
-        __half2 v = __float2half2_rn(0.f);
-        if (row_ok && ((col_ok >> j) & 1u)) v = __ldg(rowp + j * cp_count);
-        xv[j] = __half22float2(v);
+        for (int j = 0; j < IN_COLS; ++j) xv[j] = __half22float2(__ldg(rowp + j * cp_count));
+        rowp += row_stride;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          const int ky = ir - r * S;
+          if (ky >= 0 && ky < K) {
+#pragma unroll
+            for (int tx = 0; tx < TW; ++tx)
+#pragma unroll
+              for (int kx = 0; kx < K; ++kx)
+                acc[r][tx] = __ffma2_rn(xv[tx * S + kx], wreg[ky * K + kx], acc[r][tx]);
+          }
+        }
       }
-      // input row ir feeds output row r through tap ky = ir - r*S
+    } else {
+      unsigned col_ok = 0;
 #pragma unroll
-      for (int r = 0; r < ROWS; ++r) {
-        const int ky = ir - r * S;
-        if (ky >= 0 && ky < K) {
+      for (int j = 0; j < IN_COLS; ++j)
+        if (ix0 + j >= 0 && ix0 + j < wd) col_ok |= 1u << j;
 #pragma unroll
-          for (int tx = 0; tx < TW; ++tx)
+      for (int ir = 0; ir < IN_ROWS; ++ir) {
+        const int iy = iy0 + ir;
+        const bool row_ok = (iy >= 0) && (iy < h);
+        float2 xv[IN_COLS];
 #pragma unroll
-            for (int kx = 0; kx < K; ++kx)
-              acc[r][tx] = __ffma2_rn(xv[tx * S + kx], wreg[ky * K + kx], acc[r][tx]);
+        for (int j = 0; j < IN_COLS; ++j) {
+          __half2 v = __float2half2_rn(0.f);
+          if (row_ok && ((col_ok >> j) & 1u)) v = __ldg(rowp + j * cp_count);
+          xv[j] = __half22float2(v);
+        }
+        rowp += row_stride;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          const int ky = ir - r * S;
+          if (ky >= 0 && ky < K) {
+#pragma unroll
+            for (int tx = 0; tx < TW; ++tx)
+#pragma unroll
+              for (int kx = 0; kx < K; ++kx)
+                acc[r][tx] = __ffma2_rn(xv[tx * S + kx], wreg[ky * K + kx], acc[r][tx]);
+          }
         }
       }
     }
@@ -99,24 +124,20 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
     float2 bv = make_float2(0.f, 0.f);
     if (HAS_BIAS) bv = __ldg(reinterpret_cast<const float2*>(bias) + cp);
     __half2* out2 = reinterpret_cast<__half2*>(out) + static_cast<size_t>(n) * ho * wo * cp_count + cp;
+    __half2* orow = out2 + (oy0 * wo + ox0) * cp_count;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      const int oy = oy0 + r;
-      if (oy < ho) {
+      if (interior || oy0 + r < ho) {
 #pragma unroll
         for (int tx = 0; tx < TW; ++tx) {
-          const int ox = ox0 + tx;
-          if (ox < wo) {
-            const float o0 = apply_act_t<ACT>(acc[r][tx].x + bv.x);
-            const float o1 = apply_act_t<ACT>(acc[r][tx].y + bv.y);
-            if (HAS_SE) {
-              ssum.x += o0;
-              ssum.y += o1;
-            }
-            out2[(oy * wo + ox) * cp_count] = __floats2half2_rn(o0, o1);
+          if (interior || ox0 + tx < wo) {
+            const float2 o = apply_act2<ACT>(__fadd2_rn(acc[r][tx], bv));
+            if (HAS_SE) ssum = __fadd2_rn(ssum, o);
+            orow[tx * cp_count] = __floats2half2_rn(o.x, o.y);
           }
         }
       }
+      orow += wo * cp_count;
     }
   }
 
@@ -146,27 +167,24 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
   }
 }
 
-// SE gate: gridDim.x = images, gridDim.y = slices of the project-weight slab.
+// SE gate: one CTA per image.
 //   mean[c] = inv_hw * se_sum[n][c] / 2^20
 //   r[j]    = act(b1[j] + sum_c w1[j][c] * mean[c])
-//   gate[c] = sigmoid(b2[c] + sum_j w2[c][j] * r[j])
-//   wt_scaled[n][o][c] = wt[o][c] * gate[c]
-// The y == 0 CTAs also clear `zero_buf` (the squeeze accumulator the NEXT block will use).
+//   gate[c] = sigmoid(b2[c] + sum_j w2t[j][c] * r[j])
+// and clears `zero_buf` (the squeeze accumulator the NEXT block will use).
 __global__ void __launch_bounds__(256)
-se_fc_kernel(const long long* __restrict__ se_sum, float inv_hw, const float* __restrict__ w1,
-             const float* __restrict__ b1, const float* __restrict__ w2,
-             const float* __restrict__ b2, float* __restrict__ gate,
-             const __half* __restrict__ wt, __half* __restrict__ wt_scaled,
-             long long* __restrict__ zero_buf, int zero_count, int c, int se, int nout, int act) {
+se_gate_kernel(const long long* __restrict__ se_sum, float inv_hw, const float* __restrict__ w1,
+               const float* __restrict__ b1, const float* __restrict__ w2t,
+               const float* __restrict__ b2, float* __restrict__ gate,
+               long long* __restrict__ zero_buf, int zero_count, int c, int se, int act) {
   extern __shared__ float sm[];
   float* mean = sm;        // [c]
   float* red = sm + c;     // [se]
-  float* g = red + se;     // [c]
   const int n = blockIdx.x;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x)
     mean[ch] = static_cast<float>(static_cast<double>(se_sum[static_cast<size_t>(n) * c + ch]) *
                                   (1.0 / kSeFixedScale) * static_cast<double>(inv_hw));
-  if (blockIdx.y == 0 && zero_buf != nullptr) {
+  if (zero_buf != nullptr) {
     for (int i = threadIdx.x; i < zero_count; i += blockDim.x)
       zero_buf[static_cast<size_t>(n) * zero_count + i] = 0;
   }
@@ -182,28 +200,28 @@ se_fc_kernel(const long long* __restrict__ se_sum, float inv_hw, const float* __
   __syncthreads();
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     float s = b2[ch];
-    for (int j = 0; j < se; ++j) s = fmaf(w2[static_cast<size_t>(ch) * se + j], red[j], s);
-    const float gv = 1.0f / (1.0f + expf(-s));
-    g[ch] = gv;
-    if (blockIdx.y == 0) gate[static_cast<size_t>(n) * c + ch] = gv;
+    for (int j = 0; j < se; ++j) s = fmaf(w2t[static_cast<size_t>(j) * c + ch], red[j], s);
+    gate[static_cast<size_t>(n) * c + ch] = 1.0f / (1.0f + expf(-s));
   }
-  __syncthreads();
-  if (wt != nullptr) {
-    const int cg = c >> 3;
-    const int total = nout * cg;
-    __half* dst = wt_scaled + static_cast<size_t>(n) * nout * c;
-    // the weight slab is split over gridDim.y CTAs (each recomputed the tiny gate above)
-    const int per = (total + gridDim.y - 1) / gridDim.y;
-    const int i_end = min(total, static_cast<int>(blockIdx.y + 1) * per);
-    for (int i = blockIdx.y * per + threadIdx.x; i < i_end; i += blockDim.x) {
-      const int gidx = i % cg;
-      float f[8];
-      half8_to_float(__ldg(reinterpret_cast<const uint4*>(wt) + i), f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] *= g[gidx * 8 + e];
-      reinterpret_cast<uint4*>(dst)[i] = float_to_half8(f);
-    }
-  }
+}
+
+// Excitation folded into the project weights: wt_scaled[n][o][c] = wt[o][c] * gate[n][c].
+__global__ void __launch_bounds__(256)
+se_scale_kernel(const float* __restrict__ gate, const __half* __restrict__ wt,
+                __half* __restrict__ wt_scaled, int c, int nout) {
+  const int n = blockIdx.y;
+  const int cg = c >> 3;
+  const int total = nout * cg;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int gidx = i % cg;
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(n) * c) + gidx * 2);
+  const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(n) * c) + gidx * 2 + 1);
+  float f[8];
+  half8_to_float(__ldg(reinterpret_cast<const uint4*>(wt) + i), f);
+  f[0] *= g0.x; f[1] *= g0.y; f[2] *= g0.z; f[3] *= g0.w;
+  f[4] *= g1.x; f[5] *= g1.y; f[6] *= g1.z; f[7] *= g1.w;
+  reinterpret_cast<uint4*>(wt_scaled + static_cast<size_t>(n) * nout * c)[i] = float_to_half8(f);
 }
 
 template <int K, int S>
@@ -260,17 +278,17 @@ extern "C" int edet_se_fc(const int64_t* se_sum, float inv_hw, const float* w1, 
   EDET_CHECK_ARG(se_sum && w1 && b1 && w2 && b2 && gate, "se_fc: null pointer");
   EDET_CHECK_ARG(n > 0 && c > 0 && c % 8 == 0 && se > 0, "se_fc: bad shape");
   EDET_CHECK_ARG(!wt || (wt_scaled && nout > 0), "se_fc: wt given without wt_scaled/nout");
-  const size_t smem = static_cast<size_t>(2 * c + se) * sizeof(float);
+  const size_t smem = static_cast<size_t>(c + se) * sizeof(float);
   EDET_CHECK_ARG(smem <= 48 * 1024, "se_fc: c too large");
-  int nsplit = 1;
-  if (wt) {
-    nsplit = (nout * (c >> 3)) / (256 * 8);
-    nsplit = nsplit < 1 ? 1 : (nsplit > 64 ? 64 : nsplit);
-  }
-  se_fc_kernel<<<dim3(n, nsplit), 256, smem, as_stream(stream)>>>(
+  se_gate_kernel<<<n, 256, smem, as_stream(stream)>>>(
       reinterpret_cast<const long long*>(se_sum), inv_hw, w1, b1, w2, b2, gate,
-      reinterpret_cast<const __half*>(wt), reinterpret_cast<__half*>(wt_scaled),
-      reinterpret_cast<long long*>(zero_buf), zero_count, c, se, nout, act);
+      reinterpret_cast<long long*>(zero_buf), zero_count, c, se, act);
+  EDET_CHECK_LAUNCH();
+  if (wt) {
+    const int total = nout * (c >> 3);
+    se_scale_kernel<<<dim3(ceil_div(total, 256), n), 256, 0, as_stream(stream)>>>(
+        gate, reinterpret_cast<const __half*>(wt), reinterpret_cast<__half*>(wt_scaled), c, nout);
+  }
   EDET_CHECK_LAUNCH();
   return EDET_OK;
 }

@@ -39,7 +39,7 @@ constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 113 * 1024;                    // two CTAs per SM share the 227 KiB
 
 struct Params {
-  int batch, rows, k, nout;
+  int batch, rows, k, nout, nout_pad8;
   int block_n, num_m_blocks, num_n_blocks, num_k_blocks, num_stages;
   int wbatch, ldr, tmem_cols;
   int total_tiles;
@@ -280,22 +280,21 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else {
     // ===================== Epilogue (warps 2..9) =====================
-    const int e_tid = threadIdx.x - 64;       // 0..255
+    // Fully decoupled warps: warp (quarter, team) owns rows quarter*32..+31 of the tile and the
+    // 64-column store chunks c == team (mod 2).  Each warp has a private 4 KiB staging slab and
+    // issues its own TMA stores ([32 rows x 64 cols] boxes), so the only synchronisation in the
+    // epilogue is the TMEM full/empty handshake with the MMA warp.
+    const int e_warp = warp - 2;              // 0..7
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    const int half_id = (warp - 2) >> 2;      // which 32-column half of a store chunk
+    const int team = e_warp >> 2;             // even / odd store chunks
     const int row_in_tile = quarter * 32 + lane;
+    uint8_t* my_stage = smem_store + e_warp * (32 * 128);
     int iter = 0;
-    int store_iter = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++iter) {
       const TileCoord tc = decode_tile(t, p);
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
       const int n0 = tc.n_blk * p.block_n;
-      float* bias_s = smem_bias + as * 256;
-      for (int j = e_tid; j < p.block_n; j += kEpiThreads) {
-        const int col = n0 + j;
-        bias_s[j] = (col < p.nout) ? __ldg(p.bias + col) : 0.f;
-      }
       const int row = tc.m_blk * BLOCK_M + row_in_tile;
       const bool row_ok = row < p.rows;
       const __half* res_row = nullptr;
@@ -308,63 +307,82 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       // 16-column TMEM load granule); the rest of a ragged last N tile is skipped
       const int n_valid = min(p.block_n, ((p.nout - n0 + 15) >> 4) << 4);
       const int num_chunks = (n_valid + kStoreCols - 1) / kStoreCols;
-      for (int c = 0; c < num_chunks; ++c, ++store_iter) {
+      // last chunk this warp reads from TMEM (then the accumulator can be handed back)
+      int my_last = -1;
+      for (int c = team; c < num_chunks; c += 2) my_last = c;
+      if (my_last < 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+      }
+      for (int c = team; c < num_chunks; c += 2) {
         const int cols = min(kStoreCols, n_valid - c * kStoreCols);  // multiple of 16
-        const int sb = store_iter % kStoreStages;
-        uint8_t* stage_buf = smem_store + sb * kStoreBytes;
-        if (e_tid == 0) tma_store_wait_read<kStoreStages - 1>();
-        epi_barrier();  // staging buffer free; bias_s visible
-        const int c_lo = half_id * 32;            // this warp's columns inside the chunk
-        float v[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>(as * p.block_n + c * kStoreCols + c_lo);
+        if (lane == 0) tma_store_wait_read<0>();   // my previous store has left the slab
+        __syncwarp();
+        uint8_t* row_base = my_stage + lane * 128;
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (c_lo + g * 16 < cols) tc_ld16(taddr + g * 16, v + g * 16);
-        }
-        tc_wait_ld();
-        if (c == num_chunks - 1) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
-        }
-        uint8_t* row_base = stage_buf + row_in_tile * 128;
+        for (int hf = 0; hf < 2; ++hf) {
+          const int c_lo = hf * 32;
+          if (c_lo >= cols) break;
+          float v[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                 static_cast<uint32_t>(as * p.block_n + c * kStoreCols + c_lo);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          if (c_lo + jj * 8 < cols) {
-            const float* bsrc = bias_s + c * kStoreCols + c_lo + jj * 8;
-            const float4 b0 = *reinterpret_cast<const float4*>(bsrc);
-            const float4 b1 = *reinterpret_cast<const float4*>(bsrc + 4);
-            float2 o2[4];
-            o2[0] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 0], v[jj * 8 + 1]), make_float2(b0.x, b0.y)));
-            o2[1] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 2], v[jj * 8 + 3]), make_float2(b0.z, b0.w)));
-            o2[2] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 4], v[jj * 8 + 5]), make_float2(b1.x, b1.y)));
-            o2[3] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 6], v[jj * 8 + 7]), make_float2(b1.z, b1.w)));
-            float o[8] = {o2[0].x, o2[0].y, o2[1].x, o2[1].y, o2[2].x, o2[2].y, o2[3].x, o2[3].y};
-            if (HAS_RES) {
+          for (int g = 0; g < 2; ++g) {
+            if (c_lo + g * 16 < cols) tc_ld16(taddr + g * 16, v + g * 16);
+          }
+          tc_wait_ld();
+          if (c == my_last && (hf == 1 || c_lo + 32 >= cols)) {
+            // all TMEM reads of this warp for this accumulator are done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            if (c_lo + jj * 8 < cols) {
               const int col = n0 + c * kStoreCols + c_lo + jj * 8;
-              if (row_ok && col < p.nout) {
-                float r[8];
-                half8_to_float(ldg_nc_v4(res_row + col), r);
+              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+              if (col < p.nout_pad8) {          // a whole group of 8 biases is in bounds
+                b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+              } else if (col < p.nout) {        // ragged last group (nout % 8 != 0)
+                float bb[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] += r[e];
+                for (int e = 0; e < 8; ++e) bb[e] = (col + e < p.nout) ? __ldg(p.bias + col + e) : 0.f;
+                b0 = make_float4(bb[0], bb[1], bb[2], bb[3]);
+                b1 = make_float4(bb[4], bb[5], bb[6], bb[7]);
               }
+              float2 o2[4];
+              o2[0] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 0], v[jj * 8 + 1]), make_float2(b0.x, b0.y)));
+              o2[1] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 2], v[jj * 8 + 3]), make_float2(b0.z, b0.w)));
+              o2[2] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 4], v[jj * 8 + 5]), make_float2(b1.x, b1.y)));
+              o2[3] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 6], v[jj * 8 + 7]), make_float2(b1.z, b1.w)));
+              float o[8] = {o2[0].x, o2[0].y, o2[1].x, o2[1].y, o2[2].x, o2[2].y, o2[3].x, o2[3].y};
+              if (HAS_RES) {
+                if (row_ok && col < p.nout) {
+                  float r[8];
+                  half8_to_float(ldg_nc_v4(res_row + col), r);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) o[e] += r[e];
+                }
+              }
+              const uint4 packed = float_to_half8(o);
+              const int chunk16 = hf * 4 + jj;   // 16-byte piece inside the 128-byte row
+              *reinterpret_cast<uint4*>(row_base + ((chunk16 ^ (lane & 7)) << 4)) = packed;
             }
-            const uint4 packed = float_to_half8(o);
-            const int chunk16 = half_id * 4 + jj;   // 16-byte piece inside the 128-byte row
-            *reinterpret_cast<uint4*>(row_base + ((chunk16 ^ (row_in_tile & 7)) << 4)) = packed;
           }
         }
         fence_proxy_async_smem();
-        epi_barrier();
-        if (e_tid == 0) {
-          tma_store_3d(&map_o, smem_u32(stage_buf), n0 + c * kStoreCols, tc.m_blk * BLOCK_M, tc.b);
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&map_o, smem_u32(my_stage), n0 + c * kStoreCols,
+                       tc.m_blk * BLOCK_M + quarter * 32, tc.b);
           tma_store_commit();
         }
       }
     }
-    if (e_tid == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -454,6 +472,7 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   p.rows = rows;
   p.k = k;
   p.nout = nout;
+  p.nout_pad8 = nout & ~7;   // whole float4 pairs of bias that are in bounds
   p.block_n = pick_block_n(nout);
   p.num_m_blocks = ceil_div(rows, BLOCK_M);
   p.num_n_blocks = ceil_div(nout, p.block_n);
@@ -481,7 +500,7 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
     return rc;
   if ((rc = make_map(&mw, wt, k, nout, wbatch, k, static_cast<uint64_t>(nout) * k, p.block_n)))
     return rc;
-  if ((rc = make_map(&mo, out, nout, rows, batch, ldo, static_cast<uint64_t>(rows) * ldo, BLOCK_M)))
+  if ((rc = make_map(&mo, out, nout, rows, batch, ldo, static_cast<uint64_t>(rows) * ldo, 32)))
     return rc;
 
   static int sm_count = 0;

@@ -87,11 +87,12 @@ class Engine(object):
     self.buffers[name] = t
     return t
 
-  def _add(self, name, fn, kind='other', nbytes=0, flops=0):
+  def _add(self, name, fn, kind='other', nbytes=0, flops=0, kernels=1):
     """kind groups launches of the same kernel; nbytes / flops are the ALGORITHMIC HBM bytes
     and floating-point operations of the launch (SURVEY.md 8d formulas), used by bench.py."""
     self._ops.append((name, fn))
-    self.op_info.append({'name': name, 'kind': kind, 'bytes': int(nbytes), 'flops': int(flops)})
+    self.op_info.append({'name': name, 'kind': kind, 'bytes': int(nbytes), 'flops': int(flops),
+                         'kernels': int(kernels)})
 
   def _pw(self, name, a, wt, bias, out, act, residual=None, batch=1, rows=None, nout=None):
     if rows is None:
@@ -142,7 +143,8 @@ class Engine(object):
     se_index = 0
     if any(b.se_filters for b in a.blocks):
       # one explicit clear per forward keeps the ping-pong valid for any number of SE blocks
-      self._add('se_clear', lambda t=se_acc[0]: t.zero_(), kind='memset', nbytes=8 * n * max_mid)
+      self._add('se_clear', lambda t=se_acc[0]: t.zero_(), kind='memset', nbytes=8 * n * max_mid,
+                kernels=0)   # torch fill kernel, not one of ours
     for b in a.blocks:
       scope = '%s/%s' % (bb, b.name)
       check_c(b.input_filters, scope); check_c(b.mid_filters, scope); check_c(b.output_filters, scope)
@@ -187,7 +189,7 @@ class Engine(object):
       if b.se_filters:
         w1 = self._dev(np.asarray(w[scope + '/se/conv2d/kernel'], np.float64)[0, 0].T, f32)   # [se,C]
         b1 = self._dev(w[scope + '/se/conv2d/bias'], f32)
-        w2 = self._dev(np.asarray(w[scope + '/se/conv2d_1/kernel'], np.float64)[0, 0].T, f32)  # [C,se]
+        w2 = self._dev(np.asarray(w[scope + '/se/conv2d_1/kernel'], np.float64)[0, 0], f32)  # [se,C]
         b2 = self._dev(w[scope + '/se/conv2d_1/bias'], f32)
         gate = self._buf(b.name + '/se_gate', (n, b.mid_filters), f32)
         wt_scaled = self._buf(b.name + '/proj_w', (n, b.output_filters, b.mid_filters))
@@ -197,7 +199,8 @@ class Engine(object):
                   proj_wt=proj_wt, wt_scaled=wt_scaled, next_zero=next_zero:
                   ops.se_fc(partial, inv_hw, w1, b1, w2, b2, gate, act, proj_wt, wt_scaled,
                             next_zero),
-                  kind='se_fc', nbytes=8 * partial.numel() + 2 * proj_wt.numel() + 2 * wt_scaled.numel())
+                  kind='se_fc', nbytes=8 * partial.numel() + 2 * proj_wt.numel() + 2 * wt_scaled.numel(),
+                  kernels=2)
         self._pw(b.name + '/project', dwo, wt_scaled, proj_b, y, utils.ACT_NONE, residual=res,
                  batch=n, rows=ho * wo)
       else:
@@ -363,8 +366,8 @@ class Engine(object):
                                        self.image_id_base, self.max_output_size, iou_t, score_t,
                                        tf_sigma, (float(H), float(W)), self.detections,
                                        self.sel_index, self.valid, work),
-              kind='nms_v5', nbytes=28 * n * K)
-    self.launches_per_forward = len(self._ops)
+              kind='nms_v5', nbytes=28 * n * K, kernels=2)
+    self.launches_per_forward = sum(i['kernels'] for i in self.op_info)
 
   # ---- execution ------------------------------------------------------------------------------
   def _run_ops(self, upto=None):

@@ -30,6 +30,7 @@ import torch
 
 from automl_b200 import hparams_config
 from automl_b200 import ops
+from automl_b200 import parallel
 from automl_b200 import weights as weights_lib
 from automl_b200.arch import DetArch
 from automl_b200.engine import Engine
@@ -110,6 +111,12 @@ class ServingDriver(object):
     self.stddev_rgb = _rgb3(params['stddev_rgb'])
     self._host_det = torch.empty(self.batch_size, self.engine.max_output_size, 7).pin_memory()
     self._scales = torch.empty(self.batch_size, dtype=torch.float32).pin_memory()
+    self._gathered = None
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+      world = torch.distributed.get_world_size()
+      if world > 1:
+        self._gathered = torch.empty(world * self.batch_size, self.engine.max_output_size, 7,
+                                     device=self.device)
     self.signitures = {
         'image_files': 'image_files',     # bytes of encoded images (serve_files)
         'image_arrays': 'image_arrays',   # uint8 HxWx3 arrays (serve_images)
@@ -142,13 +149,20 @@ class ServingDriver(object):
     eng.image_scales.copy_(self._scales, non_blocking=True)
 
   def serve_images(self, image_arrays):
-    """image_arrays: list (or array) of HxWx3 uint8 images -> float32 [N, max_output_size, 7]."""
+    """image_arrays: list (or array) of HxWx3 uint8 images -> float32 [N, max_output_size, 7].
+
+    Under torch.distributed (one process per GPU, batch sharded over the ranks) the per-rank
+    detection blocks are all-gathered on the device first, so every rank returns the global
+    [world * N, max_output_size, 7] result (the single collective of the path)."""
     if self.engine is None:
       self.build()
     with torch.cuda.device(self.device):
       self._stage_raw(image_arrays)
       self.engine.run(postprocess=True)
-      self._host_det.copy_(self.engine.detections, non_blocking=True)
+      det = parallel.gather_detections(self.engine.detections, self._gathered)
+      if det.shape[0] != self._host_det.shape[0]:
+        self._host_det = torch.empty(tuple(det.shape)).pin_memory()
+      self._host_det.copy_(det, non_blocking=True)
       torch.cuda.current_stream().synchronize()
     return self._host_det.numpy().copy()
 

@@ -120,7 +120,8 @@ int edet_depthwise_conv(const edet_half* in, edet_half* out, const edet_half* w,
  *   mean = se_sum * 2^-20 * inv_hw ; s = sigmoid(W2 @ act(W1 @ mean + b1) + b2)
  *   wt_scaled[img, o, c] = wt[o, c] * s[img, c]
  * Replaces backbone/efficientnet_model.py:183-195 (SE.call) and the multiply at :195.
- *   se_sum   int64 [n, c]               w1 float32 [se][c], b1 [se], w2 float32 [c][se], b2 [c]
+ *   se_sum   int64 [n, c]               w1 float32 [se][c], b1 [se], w2 float32 [se][c] (the
+ *            second FC stored TRANSPOSED so both FCs read coalesced), b2 [c]
  *   gate     float32 [n, c] (output, always written)
  *   wt       half [nout][c] project weights (nullable -> only the gate is produced)
  *   wt_scaled half [n][nout][c]

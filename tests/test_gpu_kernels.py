@@ -142,7 +142,7 @@ def test_se_fc():
   gate = torch.empty(n, c, device=DEV)
   wt_scaled = torch.empty(n, nout, c, dtype=torch.float16, device=DEV)
   inv_hw = 1.0 / 50.0
-  ops.se_fc(se_sum.to(DEV), inv_hw, w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), gate,
+  ops.se_fc(se_sum.to(DEV), inv_hw, w1.to(DEV), b1.to(DEV), w2.T.contiguous().to(DEV), b2.to(DEV), gate,
             utils.ACT_SWISH, wt.to(DEV), wt_scaled, nxt)
   torch.cuda.synchronize()
   assert int(nxt.abs().sum()) == 0          # the next block's accumulator was cleared
