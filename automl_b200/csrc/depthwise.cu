@@ -28,7 +28,7 @@ struct DwCfg {
 // needs 25 MACs per output element, more than the scalar FFMA pipe can issue at the HBM rate,
 // and without the column tiling the half->float conversions of the kx re-reads dominate.
 template <int K, int S, int ACT, bool HAS_BIAS, bool HAS_SE>
-__global__ void __launch_bounds__(kDwThreads, 3)
+__global__ void __launch_bounds__(kDwThreads, (K == 3) ? 4 : 3)
 depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
                  const __half* __restrict__ w, const float* __restrict__ bias,
                  long long* __restrict__ se_sum, int h, int wd, int c, int ho, int wo, int pad_t,
@@ -72,12 +72,25 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
     const __half2* rowp = in2 + (iy0 * wd + ix0) * cp_count;   // may point outside; guarded below
 
     if (interior) {
+      // software pipeline: the raw loads run two input rows ahead of the arithmetic, so each
+      // thread keeps 3 rows of loads in flight (this kernel is latency bound otherwise)
+      __half2 raw[3][IN_COLS];
+#pragma unroll
+      for (int pre = 0; pre < 2; ++pre) {
+#pragma unroll
+        for (int j = 0; j < IN_COLS; ++j) raw[pre][j] = __ldg(rowp + j * cp_count);
+        rowp += row_stride;
+      }
 #pragma unroll
       for (int ir = 0; ir < IN_ROWS; ++ir) {
+        if (ir + 2 < IN_ROWS) {
+#pragma unroll
+          for (int j = 0; j < IN_COLS; ++j) raw[(ir + 2) % 3][j] = __ldg(rowp + j * cp_count);
+          rowp += row_stride;
+        }
         float2 xv[IN_COLS];
 #pragma unroll
-        for (int j = 0; j < IN_COLS; ++j) xv[j] = __half22float2(__ldg(rowp + j * cp_count));
-        rowp += row_stride;
+        for (int j = 0; j < IN_COLS; ++j) xv[j] = __half22float2(raw[ir % 3][j]);
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
           const int ky = ir - r * S;

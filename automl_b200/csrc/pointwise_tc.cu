@@ -31,16 +31,19 @@ constexpr int BLOCK_K = 64;  // 64 halves = 128 bytes = one 128B-swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int kEpiThreads = 256;
-constexpr int kStoreStages = 2;
 constexpr int kStoreCols = 64;
-constexpr int kATileBytes = BLOCK_M * BLOCK_K * 2;        // 16 KiB
-constexpr int kStoreBytes = BLOCK_M * kStoreCols * 2;     // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 113 * 1024;                    // two CTAs per SM share the 227 KiB
 
 struct Params {
   int batch, rows, k, nout, nout_pad8;
   int block_n, num_m_blocks, num_n_blocks, num_k_blocks, num_stages;
+  int block_k;        // 64 / 32 / 16 halves per k-block == 128B / 64B / 32B swizzled smem rows
+  int a_stage_bytes, b_stage_bytes;
+  int desc_sbo;       // byte distance between 8-row groups in smem (8 * row pitch)
+  int desc_layout;    // UMMA layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+  int slabs_per_warp; // private TMA-store staging slabs per epilogue warp (1 or 2)
+  int accum_stages;   // TMEM accumulator stages (2 when 2*block_n <= 256 columns, else 1)
   int wbatch, ldr, tmem_cols;
   int total_tiles;
   const float* bias;
@@ -145,13 +148,15 @@ __device__ __forceinline__ void epi_barrier() {
 // K-major, 128B-swizzled smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 1024>>4 | version [46,48) = 1 |
 // layout [61,64) = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+// The 64B / 32B swizzle variants (layout 4 / 6, SBO 512 / 256) are used for the thin-K layers
+// (K <= 32 / K <= 16) so that a pipeline stage only holds the bytes that exist.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int sbo, int layout) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout) << 61;
   return d;
 }
 
@@ -176,9 +181,9 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
   // 1024-byte alignment for the swizzle atoms.
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int stage_bytes = kATileBytes + p.block_n * BLOCK_K * 2;
+  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   uint8_t* smem_store = smem + p.num_stages * stage_bytes;
-  float* smem_bias = reinterpret_cast<float*>(smem_store + kStoreStages * kStoreBytes);  // [2][256]
+  float* smem_bias = reinterpret_cast<float*>(smem_store + p.slabs_per_warp * (kEpiThreads / 32) * 4096);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + 2 * 256);
   uint64_t* full_bar = bars;                       // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]
@@ -221,7 +226,8 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
+      // bytes the two TMA boxes deliver (the B slot may be padded to 1 KiB)
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.a_stage_bytes + p.block_n * p.block_k * 2);
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(t, p);
         const int wb = (p.wbatch > 1) ? tc.b : 0;
@@ -230,9 +236,9 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, tx_bytes);
           uint8_t* sa = smem + stage * stage_bytes;
-          tma_load_3d(smem_u32(sa), &map_a, fb, kb * BLOCK_K, tc.m_blk * BLOCK_M, tc.b);
-          tma_load_3d(smem_u32(sa + kATileBytes), &map_w, fb, kb * BLOCK_K, tc.n_blk * p.block_n,
-                      wb);
+          tma_load_3d(smem_u32(sa), &map_a, fb, kb * p.block_k, tc.m_blk * BLOCK_M, tc.b);
+          tma_load_3d(smem_u32(sa + p.a_stage_bytes), &map_w, fb, kb * p.block_k,
+                      tc.n_blk * p.block_n, wb);
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
@@ -251,8 +257,8 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       uint32_t phase = 0;
       int iter = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++iter) {
-        const int as = iter & 1;
-        const uint32_t aphase = (iter >> 1) & 1;
+        const int as = p.accum_stages == 2 ? (iter & 1) : 0;
+        const uint32_t aphase = p.accum_stages == 2 ? ((iter >> 1) & 1) : (iter & 1);
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * p.block_n);
@@ -260,10 +266,10 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           uint8_t* sa = smem + stage * stage_bytes;
-          const uint64_t da = make_smem_desc(smem_u32(sa));
-          const uint64_t db = make_smem_desc(smem_u32(sa + kATileBytes));
-          const int k_rem = p.k - kb * BLOCK_K;
-          const int ksteps = k_rem >= BLOCK_K ? BLOCK_K / UMMA_K : (k_rem + UMMA_K - 1) / UMMA_K;
+          const uint64_t da = make_smem_desc(smem_u32(sa), p.desc_sbo, p.desc_layout);
+          const uint64_t db = make_smem_desc(smem_u32(sa + p.a_stage_bytes), p.desc_sbo, p.desc_layout);
+          const int k_rem = p.k - kb * p.block_k;
+          const int ksteps = k_rem >= p.block_k ? p.block_k / UMMA_K : (k_rem + UMMA_K - 1) / UMMA_K;
           for (int ks = 0; ks < ksteps; ++ks) {
             // advance 16 halves = 32 bytes inside the swizzle atom: +2 in the >>4 address field
             tc_mma_f16(tmem_d, da + static_cast<uint64_t>(ks * 2), db + static_cast<uint64_t>(ks * 2),
@@ -288,12 +294,13 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int team = e_warp >> 2;             // even / odd store chunks
     const int row_in_tile = quarter * 32 + lane;
-    uint8_t* my_stage = smem_store + e_warp * (32 * 128);
+    uint8_t* my_slabs = smem_store + e_warp * p.slabs_per_warp * (32 * 128);
     int iter = 0;
+    int store_cnt = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++iter) {
       const TileCoord tc = decode_tile(t, p);
-      const int as = iter & 1;
-      const uint32_t aphase = (iter >> 1) & 1;
+      const int as = p.accum_stages == 2 ? (iter & 1) : 0;
+      const uint32_t aphase = p.accum_stages == 2 ? ((iter >> 1) & 1) : (iter & 1);
       const int n0 = tc.n_blk * p.block_n;
       const int row = tc.m_blk * BLOCK_M + row_in_tile;
       const bool row_ok = row < p.rows;
@@ -317,7 +324,11 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       }
       for (int c = team; c < num_chunks; c += 2) {
         const int cols = min(kStoreCols, n_valid - c * kStoreCols);  // multiple of 16
-        if (lane == 0) tma_store_wait_read<0>();   // my previous store has left the slab
+        uint8_t* my_stage = my_slabs + (p.slabs_per_warp == 2 ? (store_cnt & 1) * 4096 : 0);
+        ++store_cnt;
+        if (lane == 0) {                           // the store that last used this slab has left it
+          if (p.slabs_per_warp == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+        }
         __syncwarp();
         uint8_t* row_base = my_stage + lane * 128;
 #pragma unroll
@@ -418,7 +429,8 @@ static EncodeTiledFn get_encode_fn() {
 
 // 3-D half tensor [d2][d1][d0] (d0 contiguous), box [1][box1][64], 128B swizzle.
 static int make_map(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
-                    uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box1) {
+                    uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box1,
+                    uint32_t box0 = BLOCK_K) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -426,10 +438,13 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1,
   }
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(BLOCK_K), box1, 1};
+  cuuint32_t box[3] = {box0, box1, 1};
+  const CUtensorMapSwizzle swz = box0 == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : box0 == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                              : CU_TENSOR_MAP_SWIZZLE_32B;
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) dims=[%llu,%llu,%llu] strides=[%llu,%llu] box1=%u",
@@ -441,11 +456,14 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1,
   return EDET_OK;
 }
 
-// N tile: at most 128 columns so that two CTAs (2 x 2 accumulator stages x 128 TMEM columns,
-// <=113 KiB smem each) are resident per SM.  Wider outputs take several N tiles; the A tile of
-// the extra tiles comes from L2, and the epilogue skips the columns past nout.
+// N tile.  Two CTAs are resident per SM (<=113 KiB smem, <=256 TMEM columns each):
+//   nout <= 128 : one tile, two accumulator stages;
+//   nout <= 256 : one tile, ONE accumulator stage (the other CTA of the SM hides the gap) --
+//                 avoids re-reading A and a ragged second tile for N = 144 / 240;
+//   wider       : tiles of 128 columns; the A tile of the extra tiles comes from L2 and the
+//                 epilogue skips the columns past nout.
 static int pick_block_n(int nout) {
-  if (nout <= 128) return ((nout + 15) / 16) * 16;
+  if (nout <= 256) return ((nout + 15) / 16) * 16;
   return 128;
 }
 
@@ -476,19 +494,32 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   p.block_n = pick_block_n(nout);
   p.num_m_blocks = ceil_div(rows, BLOCK_M);
   p.num_n_blocks = ceil_div(nout, p.block_n);
-  p.num_k_blocks = ceil_div(k, BLOCK_K);
+  // k-block / smem row pitch: 16 halves (32B swizzle) for K <= 16, 32 (64B) for K <= 32, else
+  // 64 (128B) -- unless two 64-wide stages of this (wide) N tile would not fit next to the store
+  // slabs, in which case the narrower 32-wide stages keep the pipeline >= 3 deep.
+  p.block_k = k <= 16 ? 16 : (k <= 32 ? 32 : 64);
+  if (p.block_k == 64 && 2 * (BLOCK_M + p.block_n) * 128 + 40 * 1024 > kSmemLimit) p.block_k = 32;
+  p.desc_layout = p.block_k == 64 ? 2 : (p.block_k == 32 ? 4 : 6);
+  p.desc_sbo = 8 * p.block_k * 2;
+  p.num_k_blocks = ceil_div(k, p.block_k);
+  p.a_stage_bytes = BLOCK_M * p.block_k * 2;
+  p.b_stage_bytes = ((p.block_n * p.block_k * 2 + 1023) / 1024) * 1024;
   p.wbatch = wbatch;
   p.ldr = ldr;
   p.bias = bias;
   p.residual = residual;
+  p.accum_stages = (2 * p.block_n <= 256) ? 2 : 1;
   int cols = 32;
-  while (cols < 2 * p.block_n) cols *= 2;
+  while (cols < p.accum_stages * p.block_n) cols *= 2;
   p.tmem_cols = cols;
   p.total_tiles = batch * p.num_m_blocks * p.num_n_blocks;
 
-  const int stage_bytes = kATileBytes + p.block_n * BLOCK_K * 2;
-  const int fixed = kStoreStages * kStoreBytes + 2 * 256 * 4 + (2 * kMaxStages + 4) * 8 + 16;
-  int stages = (kSmemLimit - 1024 - fixed) / stage_bytes;  // 2 (block_n 128) .. 4 (block_n 16)
+  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  // thin stages (small K) leave room for a second store slab per epilogue warp
+  p.slabs_per_warp = stage_bytes <= 16 * 1024 ? 2 : 1;
+  const int fixed = p.slabs_per_warp * (kEpiThreads / 32) * 4096 + 2 * 256 * 4 +
+                    (2 * kMaxStages + 4) * 8 + 16;
+  int stages = (kSmemLimit - 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   EDET_CHECK_ARG(stages >= 2, "pointwise_tc: block_n %d leaves <2 pipeline stages", p.block_n);
   p.num_stages = stages;
@@ -496,9 +527,11 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
 
   CUtensorMap ma, mw, mo;
   int rc;
-  if ((rc = make_map(&ma, a, k, rows, batch, lda, static_cast<uint64_t>(rows) * lda, BLOCK_M)))
+  if ((rc = make_map(&ma, a, k, rows, batch, lda, static_cast<uint64_t>(rows) * lda, BLOCK_M,
+                     p.block_k)))
     return rc;
-  if ((rc = make_map(&mw, wt, k, nout, wbatch, k, static_cast<uint64_t>(nout) * k, p.block_n)))
+  if ((rc = make_map(&mw, wt, k, nout, wbatch, k, static_cast<uint64_t>(nout) * k, p.block_n,
+                     p.block_k)))
     return rc;
   if ((rc = make_map(&mo, out, nout, rows, batch, ldo, static_cast<uint64_t>(rows) * ldo, 32)))
     return rc;
