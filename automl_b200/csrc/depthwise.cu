@@ -185,7 +185,7 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
 //   r[j]    = act(b1[j] + sum_c w1[j][c] * mean[c])
 //   gate[c] = sigmoid(b2[c] + sum_j w2t[j][c] * r[j])
 // and clears `zero_buf` (the squeeze accumulator the NEXT block will use).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 se_gate_kernel(const long long* __restrict__ se_sum, float inv_hw, const float* __restrict__ w1,
                const float* __restrict__ b1, const float* __restrict__ w2t,
                const float* __restrict__ b2, float* __restrict__ gate,
@@ -203,17 +203,41 @@ se_gate_kernel(const long long* __restrict__ se_sum, float inv_hw, const float* 
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // Both FCs are pure latency (a few thousand MACs): keep 4-8 independent loads in flight.
   for (int j = warp; j < se; j += nwarps) {
-    float s = 0.f;
-    for (int ch = lane; ch < c; ch += 32) s = fmaf(w1[static_cast<size_t>(j) * c + ch], mean[ch], s);
+    const float* wr = w1 + static_cast<size_t>(j) * c;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int ch = lane;
+    for (; ch + 96 < c; ch += 128) {
+      const float a0 = __ldg(wr + ch), a1 = __ldg(wr + ch + 32), a2 = __ldg(wr + ch + 64),
+                  a3 = __ldg(wr + ch + 96);
+      s0 = fmaf(a0, mean[ch], s0);
+      s1 = fmaf(a1, mean[ch + 32], s1);
+      s2 = fmaf(a2, mean[ch + 64], s2);
+      s3 = fmaf(a3, mean[ch + 96], s3);
+    }
+    for (; ch < c; ch += 32) s0 = fmaf(__ldg(wr + ch), mean[ch], s0);
+    float s = (s0 + s1) + (s2 + s3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) red[j] = apply_act(s + b1[j], act);
   }
   __syncthreads();
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    float s = b2[ch];
-    for (int j = 0; j < se; ++j) s = fmaf(w2t[static_cast<size_t>(j) * c + ch], red[j], s);
+    float s0 = b2[ch], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int j = 0;
+    for (; j + 3 < se; j += 4) {
+      const float a0 = __ldg(w2t + static_cast<size_t>(j) * c + ch);
+      const float a1 = __ldg(w2t + static_cast<size_t>(j + 1) * c + ch);
+      const float a2 = __ldg(w2t + static_cast<size_t>(j + 2) * c + ch);
+      const float a3 = __ldg(w2t + static_cast<size_t>(j + 3) * c + ch);
+      s0 = fmaf(a0, red[j], s0);
+      s1 = fmaf(a1, red[j + 1], s1);
+      s2 = fmaf(a2, red[j + 2], s2);
+      s3 = fmaf(a3, red[j + 3], s3);
+    }
+    for (; j < se; ++j) s0 = fmaf(__ldg(w2t + static_cast<size_t>(j) * c + ch), red[j], s0);
+    const float s = (s0 + s1) + (s2 + s3);
     gate[static_cast<size_t>(n) * c + ch] = 1.0f / (1.0f + expf(-s));
   }
 }
@@ -293,7 +317,7 @@ extern "C" int edet_se_fc(const int64_t* se_sum, float inv_hw, const float* w1, 
   EDET_CHECK_ARG(!wt || (wt_scaled && nout > 0), "se_fc: wt given without wt_scaled/nout");
   const size_t smem = static_cast<size_t>(c + se) * sizeof(float);
   EDET_CHECK_ARG(smem <= 48 * 1024, "se_fc: c too large");
-  se_gate_kernel<<<n, 256, smem, as_stream(stream)>>>(
+  se_gate_kernel<<<n, 512, smem, as_stream(stream)>>>(
       reinterpret_cast<const long long*>(se_sum), inv_hw, w1, b1, w2, b2, gate,
       reinterpret_cast<long long*>(zero_buf), zero_count, c, se, act);
   EDET_CHECK_LAUNCH();

@@ -346,27 +346,42 @@ class Engine(object):
     nms_cfg = p.nms_configs.as_dict() if hasattr(p.nms_configs, 'as_dict') else dict(p.nms_configs)
     iou_t, score_t, tf_sigma = nms_v5_params(nms_cfg)
     self.max_output_size = int(nms_cfg['max_output_size'])
-    self.boxes = self._buf('boxes', (n, K, 4), f32)
-    self.scores = self._buf('scores', (n, K), f32)
-    self.classes = self._buf('classes', (n, K), torch.int32)
+    # Two sets of post-processing buffers: NMS of step i runs on its own stream while the
+    # network of step i+1 (which writes the OTHER set) already runs on the main stream.
     self.image_scales = self._buf('image_scales', (n,), f32)
     self.image_scales.fill_(1.0)
-    self.detections = self._buf('detections', (n, self.max_output_size, 7), f32)
-    self.sel_index = self._buf('sel_index', (n, self.max_output_size), torch.int32)
-    self.valid = self._buf('valid', (n,), torch.int32)
-    work = self._buf('nms_work', (ops.nms_work_bytes(n, K),), torch.uint8)
+    self._post = []
     cls_l = [self.cls_out[l] for l in a.levels]
     box_l = [self.box_out[l] for l in a.levels]
     level_hw = [a.level_hw[l] for l in a.levels]
-    self._add('pre_nms', lambda: ops.pre_nms(cls_l, box_l, level_hw, A, C, anc, self.boxes,
-                                            self.scores, self.classes),
-              kind='pre_nms',
+    self._pre_ops, self._nms_ops = [], []
+    for sidx in range(2):
+      ps = {
+          'boxes': self._buf('boxes%d' % sidx, (n, K, 4), f32),
+          'scores': self._buf('scores%d' % sidx, (n, K), f32),
+          'classes': self._buf('classes%d' % sidx, (n, K), torch.int32),
+          'detections': self._buf('detections%d' % sidx, (n, self.max_output_size, 7), f32),
+          'sel_index': self._buf('sel_index%d' % sidx, (n, self.max_output_size), torch.int32),
+          'valid': self._buf('valid%d' % sidx, (n,), torch.int32),
+          'work': self._buf('nms_work%d' % sidx, (ops.nms_work_bytes(n, K),), torch.uint8),
+      }
+      self._post.append(ps)
+      self._pre_ops.append(lambda ps=ps: ops.pre_nms(cls_l, box_l, level_hw, A, C, anc,
+                                                     ps['boxes'], ps['scores'], ps['classes']))
+      self._nms_ops.append(lambda ps=ps: ops.nms_v5(
+          ps['boxes'], ps['scores'], ps['classes'], self.image_scales, self.image_id_base,
+          self.max_output_size, iou_t, score_t, tf_sigma, (float(H), float(W)),
+          ps['detections'], ps['sel_index'], ps['valid'], ps['work']))
+    self._cur = 0
+    self._step = 0
+    self._nms_stream = torch.cuda.Stream(device=self.device)
+    self._ev_pre = [torch.cuda.Event() for _ in range(2)]
+    self._ev_nms = [torch.cuda.Event() for _ in range(2)]
+    self._nms_pending = [False, False]
+    # op list entries (set 0) for profiling / accounting
+    self._add('pre_nms', self._pre_ops[0], kind='pre_nms',
               nbytes=2 * sum(t.numel() for t in cls_l + box_l) + 24 * n * K + 16 * K)
-    self._add('nms', lambda: ops.nms_v5(self.boxes, self.scores, self.classes, self.image_scales,
-                                       self.image_id_base, self.max_output_size, iou_t, score_t,
-                                       tf_sigma, (float(H), float(W)), self.detections,
-                                       self.sel_index, self.valid, work),
-              kind='nms_v5', nbytes=28 * n * K, kernels=2)
+    self._add('nms', self._nms_ops[0], kind='nms_v5', nbytes=28 * n * K, kernels=2)
     self.launches_per_forward = sum(i['kernels'] for i in self.op_info)
 
   # ---- execution ------------------------------------------------------------------------------
@@ -374,24 +389,87 @@ class Engine(object):
     for _, fn in (self._ops if upto is None else self._ops[:upto]):
       fn()
 
-  def run(self, postprocess=True):
-    """Enqueues one forward (+post-process) on the current stream, from self.input."""
-    upto = None if postprocess else self.num_network_ops
-    if not self.use_cuda_graph:
-      self._run_ops(upto)
-      return
-    key = bool(postprocess)
+  # buffers of the most recent post-processed step
+  @property
+  def boxes(self):
+    return self._post[self._cur]['boxes']
+
+  @property
+  def scores(self):
+    return self._post[self._cur]['scores']
+
+  @property
+  def classes(self):
+    return self._post[self._cur]['classes']
+
+  @property
+  def detections(self):
+    return self._post[self._cur]['detections']
+
+  @property
+  def sel_index(self):
+    return self._post[self._cur]['sel_index']
+
+  @property
+  def valid(self):
+    return self._post[self._cur]['valid']
+
+  def _graph_for(self, key, fn):
     if self._graph is None:
       self._graph = {}
     if key not in self._graph:
-      # warm-up outside capture (sets kernel attributes, loads modules), then capture
-      self._run_ops(upto)
+      fn()                                   # warm-up outside capture (kernel attributes, modules)
       torch.cuda.synchronize(self.device)
       g = torch.cuda.CUDAGraph()
       with torch.cuda.graph(g):
-        self._run_ops(upto)
+        fn()
       self._graph[key] = g
-    self._graph[key].replay()
+    return self._graph[key]
+
+  def run(self, postprocess=True, after_nms=None):
+    """Enqueues one forward from self.input.
+
+    postprocess=False: network only, on the current stream.
+    postprocess=True : network + pre-NMS on the current stream, then NMS (and `after_nms(dets)`,
+      e.g. the all-gather / D2H copy) on the engine's NMS stream, so consecutive steps overlap the
+      NMS of step i with the network of step i+1.  Call wait_detections() (or detect()) before
+      reading `self.detections` from the current stream.
+    """
+    net_upto = self.num_network_ops
+    if not postprocess:
+      if self.use_cuda_graph:
+        self._graph_for('net', lambda: self._run_ops(net_upto)).replay()
+      else:
+        self._run_ops(net_upto)
+      return
+    sidx = self._step % 2
+    self._step += 1
+    main = torch.cuda.current_stream(self.device)
+    if self._nms_pending[sidx]:
+      main.wait_event(self._ev_nms[sidx])      # the NMS that last read this buffer set is done
+    def net_and_pre():
+      self._run_ops(net_upto)
+      self._pre_ops[sidx]()
+    if self.use_cuda_graph:
+      self._graph_for(('net+pre', sidx), net_and_pre).replay()
+    else:
+      net_and_pre()
+    self._ev_pre[sidx].record(main)
+    with torch.cuda.stream(self._nms_stream):
+      self._nms_stream.wait_event(self._ev_pre[sidx])
+      if self.use_cuda_graph:
+        self._graph_for(('nms', sidx), self._nms_ops[sidx]).replay()
+      else:
+        self._nms_ops[sidx]()
+      if after_nms is not None:
+        after_nms(self._post[sidx]['detections'])
+      self._ev_nms[sidx].record(self._nms_stream)
+    self._nms_pending[sidx] = True
+    self._cur = sidx
+
+  def wait_detections(self):
+    """Makes the current stream wait for the NMS (and after_nms hook) of the latest step."""
+    torch.cuda.current_stream(self.device).wait_event(self._ev_nms[self._cur])
 
   def set_input(self, images):
     """images: float32 [N,H,W,3] tensor (any device) or array; copied into the static input."""
@@ -419,11 +497,12 @@ class Engine(object):
       if image_scales is not None:
         self.image_scales.copy_(torch.as_tensor(image_scales, dtype=torch.float32), non_blocking=True)
       self.run(postprocess=True)
+      self.wait_detections()
     return self.detections
 
   def nms_fallback_count(self):
     """Images of the last run that needed the full-queue NMS kernel (fast path not provable)."""
-    flags = self.buffers['nms_work'][-4 * self.n:].view(torch.int32)
+    flags = self._post[self._cur]['work'][-4 * self.n:].view(torch.int32)
     return int(flags.sum().item())
 
   def op_names(self):

@@ -158,13 +158,17 @@ class ServingDriver(object):
       self.build()
     with torch.cuda.device(self.device):
       self._stage_raw(image_arrays)
-      self.engine.run(postprocess=True)
-      det = parallel.gather_detections(self.engine.detections, self._gathered)
-      if det.shape[0] != self._host_det.shape[0]:
-        self._host_det = torch.empty(tuple(det.shape)).pin_memory()
-      self._host_det.copy_(det, non_blocking=True)
+      self.engine.run(postprocess=True, after_nms=self._gather_and_copy)
+      self.engine.wait_detections()
       torch.cuda.current_stream().synchronize()
     return self._host_det.numpy().copy()
+
+  def _gather_and_copy(self, det):
+    """Runs on the engine's NMS stream right after NMS: all-gather (multi-GPU) + D2H copy."""
+    det = parallel.gather_detections(det, self._gathered)
+    if det.shape[0] != self._host_det.shape[0]:
+      self._host_det = torch.empty(tuple(det.shape)).pin_memory()
+    self._host_det.copy_(det, non_blocking=True)
 
   def serve_files(self, image_files):
     """image_files: list of encoded image bytes (jpeg/png)."""

@@ -197,13 +197,15 @@ def main():
   w = None
   gathered = torch.empty(world * BATCH, eng.max_output_size, 7, device=dev) if world > 1 else None
 
+  gather_hook = (lambda det: parallel.gather_detections(det, gathered)) if world > 1 else None
+
   def step(e2e):
     if e2e:
       # the public call: host uint8 images in, host detections out (H2D + D2H + sync inside)
       return driver.serve_images(host_raw)
-    eng.run(postprocess=True)
-    if world > 1:  # the single collective of the path: all-gather of per-image detections
-      parallel.gather_detections(eng.detections, gathered)
+    # network + pre-NMS on the main stream; NMS (+ the single collective of the path, the
+    # all-gather of per-image detections) on the engine's NMS stream, overlapping the next step
+    eng.run(postprocess=True, after_nms=gather_hook)
     return None
 
   def timed(e2e, steps, warmup):
@@ -216,6 +218,8 @@ def main():
     e0.record()
     for _ in range(steps):
       step(e2e)
+    if not e2e:
+      eng.wait_detections()      # the last step's NMS / all-gather is inside the timed region
     e1.record()
     if world > 1:
       dist.barrier()

@@ -12,7 +12,7 @@ n = 32
 eng = Engine(c, w, n, use_cuda_graph=False)
 x = np.random.default_rng(0).uniform(0, 1, size=(n, 640, 640, 3)).astype(np.float32)
 eng.detect(torch.from_numpy(x)); torch.cuda.synchronize()
-flags = eng.buffers['nms_work'][-4 * n:].view(torch.int32).cpu().numpy()
+flags = eng._post[eng._cur]['work'][-4 * n:].view(torch.int32).cpu().numpy()
 print('fast-path reason codes per image (0 = fast path proved exact):', flags.tolist())
 print('valid:', eng.valid.cpu().numpy().tolist())
 nms = [fn for name, fn in eng._ops if name == 'nms'][0]
