@@ -37,6 +37,8 @@ template <int ACT>
 __global__ void __launch_bounds__(kFuseThreads)
 fuse_dw_kernel(const FuseParams p, const __half* __restrict__ dw_w, __half* __restrict__ out,
                int h, int wd, int c, int chunks) {
+  pdl_launch_dependents();
+  pdl_wait_prior();
   constexpr int HT = kFuseTH + 2, WT = kFuseTW + 2, G = kFuseCB / 8;
   __shared__ __align__(16) float fused[HT * WT][kFuseCB];
   const int n = blockIdx.z / chunks;
@@ -126,6 +128,8 @@ __global__ void __launch_bounds__(256)
 max_pool_kernel(const __half* __restrict__ in, __half* __restrict__ out, int h, int wd, int c,
                 int ho, int wo, int pool_h, int pool_w, int stride_h, int stride_w, int pad_t,
                 int pad_l, long long total) {
+  pdl_launch_dependents();
+  pdl_wait_prior();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cg = c >> 3;
@@ -196,17 +200,18 @@ extern "C" int edet_fuse_dw(const edet_fuse_input* h_inputs, int n_inputs, const
   const __half* hw = reinterpret_cast<const __half*>(dw_w);
   __half* ho = reinterpret_cast<__half*>(out);
   cudaStream_t s = as_stream(stream);
+  cudaError_t err = cudaSuccess;
   switch (act) {
-    case EDET_ACT_SWISH: fuse_dw_kernel<EDET_ACT_SWISH><<<grid, kFuseThreads, 0, s>>>(p, hw, ho, h, wd, c, chunks); break;
-    case EDET_ACT_RELU6: fuse_dw_kernel<EDET_ACT_RELU6><<<grid, kFuseThreads, 0, s>>>(p, hw, ho, h, wd, c, chunks); break;
-    case EDET_ACT_RELU: fuse_dw_kernel<EDET_ACT_RELU><<<grid, kFuseThreads, 0, s>>>(p, hw, ho, h, wd, c, chunks); break;
-    case EDET_ACT_HSWISH: fuse_dw_kernel<EDET_ACT_HSWISH><<<grid, kFuseThreads, 0, s>>>(p, hw, ho, h, wd, c, chunks); break;
-    case EDET_ACT_NONE: fuse_dw_kernel<EDET_ACT_NONE><<<grid, kFuseThreads, 0, s>>>(p, hw, ho, h, wd, c, chunks); break;
+    case EDET_ACT_SWISH: err = launch_pdl(fuse_dw_kernel<EDET_ACT_SWISH>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break;
+    case EDET_ACT_RELU6: err = launch_pdl(fuse_dw_kernel<EDET_ACT_RELU6>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break;
+    case EDET_ACT_RELU: err = launch_pdl(fuse_dw_kernel<EDET_ACT_RELU>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break;
+    case EDET_ACT_HSWISH: err = launch_pdl(fuse_dw_kernel<EDET_ACT_HSWISH>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break;
+    case EDET_ACT_NONE: err = launch_pdl(fuse_dw_kernel<EDET_ACT_NONE>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break;
     default:
       set_error("fuse_dw: bad activation %d", act);
       return EDET_ERR_INVALID;
   }
-  EDET_CHECK_LAUNCH();
+  EDET_CHECK_CUDA(err);
   return EDET_OK;
 }
 
@@ -220,10 +225,10 @@ extern "C" int edet_max_pool(const edet_half* in, edet_half* out, int n, int h, 
   const int ho = ceil_div(h, stride_h), wo = ceil_div(wd, stride_w);
   const long long total = static_cast<long long>(n) * ho * wo * (c >> 3);
   const int blocks = static_cast<int>((total + 255) / 256);
-  max_pool_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), h, wd, c, ho, wo, pool_h,
-      pool_w, stride_h, stride_w, same_pad_before(h, pool_h, stride_h),
-      same_pad_before(wd, pool_w, stride_w), total);
-  EDET_CHECK_LAUNCH();
+  EDET_CHECK_CUDA(launch_pdl(max_pool_kernel, dim3(blocks), dim3(256), 0, as_stream(stream),
+                             reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), h, wd,
+                             c, ho, wo, pool_h, pool_w, stride_h, stride_w,
+                             same_pad_before(h, pool_h, stride_h),
+                             same_pad_before(wd, pool_w, stride_w), total));
   return EDET_OK;
 }

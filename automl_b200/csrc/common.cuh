@@ -117,4 +117,33 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 
 inline cudaStream_t as_stream(edet_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch (PDL): every kernel of the path is launched with the
+// programmatic-stream-serialization attribute, signals `launch_dependents` as its first
+// instruction and executes `griddepcontrol.wait` before it touches global memory.  The NEXT
+// kernel's CTAs may therefore be scheduled, and run their prologue (smem carve-up, mbarrier
+// init, TMEM allocation, descriptor prefetch, weight preload into registers is NOT done before
+// the wait), while the tail of the previous kernel drains -- the step is ~220 short launches.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_prior() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace edet

@@ -33,6 +33,7 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
                  const __half* __restrict__ w, const float* __restrict__ bias,
                  long long* __restrict__ se_sum, int h, int wd, int c, int ho, int wo, int pad_t,
                  int pad_l) {
+  pdl_launch_dependents();
   constexpr int TW = kDwTW;
   constexpr int ROWS = DwCfg<K, S>::ROWS;
   constexpr int IN_ROWS = DwCfg<K, S>::IN_ROWS;
@@ -48,12 +49,14 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
   const int ox0 = xt * TW;
 
   float2 ssum = make_float2(0.f, 0.f);
+  if (!active) pdl_wait_prior();
 
   if (active) {
     const __half2* w2 = reinterpret_cast<const __half2*>(w);
     float2 wreg[K * K];
 #pragma unroll
     for (int t = 0; t < K * K; ++t) wreg[t] = __half22float2(__ldg(w2 + t * cp_count + cp));
+    pdl_wait_prior();   // the (constant) weights above were fetched during the previous kernel's tail
 
     float2 acc[ROWS][TW];
 #pragma unroll
@@ -190,6 +193,8 @@ se_gate_kernel(const long long* __restrict__ se_sum, float inv_hw, const float* 
                const float* __restrict__ b1, const float* __restrict__ w2t,
                const float* __restrict__ b2, float* __restrict__ gate,
                long long* __restrict__ zero_buf, int zero_count, int c, int se, int act) {
+  pdl_launch_dependents();
+  pdl_wait_prior();
   extern __shared__ float sm[];
   float* mean = sm;        // [c]
   float* red = sm + c;     // [se]
@@ -246,6 +251,8 @@ se_gate_kernel(const long long* __restrict__ se_sum, float inv_hw, const float* 
 __global__ void __launch_bounds__(256)
 se_scale_kernel(const float* __restrict__ gate, const __half* __restrict__ wt,
                 __half* __restrict__ wt_scaled, int c, int nout) {
+  pdl_launch_dependents();
+  pdl_wait_prior();
   const int n = blockIdx.y;
   const int cg = c >> 3;
   const int total = nout * cg;
@@ -268,8 +275,9 @@ static int launch_dw(const __half* in, __half* out, const __half* w, const float
   const int pad_t = same_pad_before(h, K, S), pad_l = same_pad_before(wd, K, S);
   dim3 grid(ceil_div(ceil_div(wo, kDwTW) * (c >> 1), kDwThreads), ceil_div(ho, DwCfg<K, S>::ROWS), n);
 #define EDET_DW_LAUNCH(ACT, HB, HS)                                                        \
-  depthwise_kernel<K, S, ACT, HB, HS><<<grid, kDwThreads, 0, stream>>>(                    \
-      in, out, w, bias, se_partial, h, wd, c, ho, wo, pad_t, pad_l)
+  launch_err = launch_pdl(depthwise_kernel<K, S, ACT, HB, HS>, grid, dim3(kDwThreads), 0,  \
+                          stream, in, out, w, bias, se_partial, h, wd, c, ho, wo, pad_t, pad_l)
+  cudaError_t launch_err = cudaSuccess;
   const bool hb = bias != nullptr, hs = se_partial != nullptr;
   if (act == EDET_ACT_SWISH && hb && hs) EDET_DW_LAUNCH(EDET_ACT_SWISH, true, true);
   else if (act == EDET_ACT_SWISH && hb && !hs) EDET_DW_LAUNCH(EDET_ACT_SWISH, true, false);
@@ -282,7 +290,7 @@ static int launch_dw(const __half* in, __half* out, const __half* w, const float
     return EDET_ERR_UNSUPPORTED;
   }
 #undef EDET_DW_LAUNCH
-  EDET_CHECK_LAUNCH();
+  EDET_CHECK_CUDA(launch_err);
   return EDET_OK;
 }
 
@@ -317,14 +325,15 @@ extern "C" int edet_se_fc(const int64_t* se_sum, float inv_hw, const float* w1, 
   EDET_CHECK_ARG(!wt || (wt_scaled && nout > 0), "se_fc: wt given without wt_scaled/nout");
   const size_t smem = static_cast<size_t>(c + se) * sizeof(float);
   EDET_CHECK_ARG(smem <= 48 * 1024, "se_fc: c too large");
-  se_gate_kernel<<<n, 512, smem, as_stream(stream)>>>(
-      reinterpret_cast<const long long*>(se_sum), inv_hw, w1, b1, w2, b2, gate,
-      reinterpret_cast<long long*>(zero_buf), zero_count, c, se, act);
-  EDET_CHECK_LAUNCH();
+  EDET_CHECK_CUDA(launch_pdl(se_gate_kernel, dim3(n), dim3(512), smem, as_stream(stream),
+                             reinterpret_cast<const long long*>(se_sum), inv_hw, w1, b1, w2, b2, gate,
+                             reinterpret_cast<long long*>(zero_buf), zero_count, c, se, act));
   if (wt) {
     const int total = nout * (c >> 3);
-    se_scale_kernel<<<dim3(ceil_div(total, 256), n), 256, 0, as_stream(stream)>>>(
-        gate, reinterpret_cast<const __half*>(wt), reinterpret_cast<__half*>(wt_scaled), c, nout);
+    EDET_CHECK_CUDA(launch_pdl(se_scale_kernel, dim3(ceil_div(total, 256), n), dim3(256), 0,
+                               as_stream(stream), static_cast<const float*>(gate),
+                               reinterpret_cast<const __half*>(wt),
+                               reinterpret_cast<__half*>(wt_scaled), c, nout));
   }
   EDET_CHECK_LAUNCH();
   return EDET_OK;

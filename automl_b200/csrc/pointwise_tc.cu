@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                     const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_o, const Params p) {
+  pdl_launch_dependents();   // the next kernel may start its prologue while this one runs
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the swizzle atoms.
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -220,6 +221,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait_prior();          // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -477,8 +479,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMa
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     configured_smem = kSmemLimit;
   }
-  kern<<<grid, kThreads, smem_bytes, stream>>>(ma, mw, mo, p);
-  EDET_CHECK_LAUNCH();
+  EDET_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem_bytes, stream, ma, mw, mo, p));
   return EDET_OK;
 }
 

@@ -28,6 +28,8 @@ struct PreParams {
 __global__ void __launch_bounds__(kPreThreads)
 pre_nms_kernel(const PreParams p, const float* __restrict__ anchors, float* __restrict__ boxes,
                float* __restrict__ scores, int32_t* __restrict__ classes) {
+  pdl_launch_dependents();
+  pdl_wait_prior();
   extern __shared__ __align__(16) uint8_t pre_smem[];
   __half* cls_s = reinterpret_cast<__half*>(pre_smem);
   int l = 0;
@@ -751,9 +753,8 @@ extern "C" int edet_pre_nms(const edet_half* const* h_cls, const edet_half* cons
   if (smem > 48 * 1024)
     EDET_CHECK_CUDA(cudaFuncSetAttribute(pre_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
-  pre_nms_kernel<<<dim3(blocks, n), kPreThreads, smem, as_stream(stream)>>>(p, anchors, boxes,
-                                                                            scores, classes);
-  EDET_CHECK_LAUNCH();
+  EDET_CHECK_CUDA(launch_pdl(pre_nms_kernel, dim3(blocks, n), dim3(kPreThreads), smem,
+                             as_stream(stream), p, anchors, boxes, scores, classes));
   return EDET_OK;
 }
 

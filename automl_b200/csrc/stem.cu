@@ -1,83 +1,102 @@
-// Stem: Conv2D 3x3 stride 2 'SAME', 3 -> cout (32..64), + folded BN + activation.
+// Stem: Conv2D 3x3 stride 2 'SAME', 3 -> cout (24..64), + folded BN + activation.
 // Reads the float32 NHWC image the reference feeds the network (efficientnet_model.py:526-527)
-// and writes NHWC fp16.  Memory-bound (K = 27): bytes = 12*n*h*w + 2*n*ho*wo*cout.
+// and writes NHWC fp16.  bytes = 12*n*h*w + 2*n*ho*wo*cout; 27 MACs per output element, so the
+// arithmetic runs on the packed fp32 pipe (FFMA2) to stay under the HBM time.
 //
-// One thread = one output pixel x all output channels; the [27][cout] weights sit in shared
-// memory as fp32 and are read as warp-wide broadcasts.
+// One thread = two horizontally adjacent output pixels x 16 output channels (8 channel pairs);
+// the [27][16] weight slab of the channel half sits in shared memory as float2 pairs and is read
+// as warp-wide broadcasts, each read feeding both pixels.
 #include "common.cuh"
 
 namespace edet {
 
 constexpr int kStemThreads = 128;
-constexpr int kStemMaxC = 64;
+constexpr int kStemCh = 16;   // output channels per thread
 
-template <int COUT, int ACT>
+template <int ACT>
 __global__ void __launch_bounds__(kStemThreads)
 stem_kernel(const float* __restrict__ in, __half* __restrict__ out, const __half* __restrict__ w,
-            const float* __restrict__ bias, int h, int wd, int ho, int wo, int pad_t, int pad_l) {
-  __shared__ float ws[27][COUT];
-  __shared__ float bs[COUT];
-  for (int i = threadIdx.x; i < 27 * COUT; i += kStemThreads)
-    ws[i / COUT][i % COUT] = __half2float(w[i]);
-  for (int i = threadIdx.x; i < COUT; i += kStemThreads) bs[i] = bias[i];
+            const float* __restrict__ bias, int h, int wd, int ho, int wo, int cout, int pad_t,
+            int pad_l) {
+  pdl_launch_dependents();
+  __shared__ __align__(16) float2 ws[27][kStemCh / 2];
+  __shared__ __align__(16) float2 bs[kStemCh / 2];
+  const int c0 = blockIdx.y * kStemCh;
+  const int cn = min(kStemCh, cout - c0);            // channels of this slab that exist (mult. of 8)
+  for (int i = threadIdx.x; i < 27 * kStemCh; i += kStemThreads) {
+    const int t = i / kStemCh, c = i % kStemCh;
+    reinterpret_cast<float*>(&ws[t][0])[c] = c < cn ? __half2float(w[t * cout + c0 + c]) : 0.f;
+  }
+  for (int i = threadIdx.x; i < kStemCh; i += kStemThreads)
+    reinterpret_cast<float*>(&bs[0])[i] = i < cn ? bias[c0 + i] : 0.f;
   __syncthreads();
+  pdl_wait_prior();   // weights staged above; the image is read below
   const int n = blockIdx.z;
-  const int p = blockIdx.x * kStemThreads + threadIdx.x;
-  if (p >= ho * wo) return;
-  const int oy = p / wo, ox = p - oy * wo;
-  float x[27];
+  const int wo2 = (wo + 1) >> 1;                      // pixel pairs per output row
   const float* in_n = in + static_cast<size_t>(n) * h * wd * 3;
+  // grid-stride loop over pixel pairs: the weight slab is staged once per CTA
+  for (int pp = blockIdx.x * kStemThreads + threadIdx.x; pp < ho * wo2;
+       pp += gridDim.x * kStemThreads) {
+    const int oy = pp / wo2, ox = (pp - oy * wo2) * 2;
+    // input patch: 3 rows x 5 columns x 3 channels (columns 0..2 feed pixel 0, 2..4 pixel 1)
+    float x[3][5][3];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int iy = oy * 2 - pad_t + ky;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - pad_t + ky;
+      const bool row_ok = iy >= 0 && iy < h;
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = ox * 2 - pad_l + kx;
-      const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < wd;
-      const float* px = in_n + (static_cast<size_t>(iy) * wd + ix) * 3;
+      for (int j = 0; j < 5; ++j) {
+        const int ix = ox * 2 - pad_l + j;
+        const bool ok = row_ok && ix >= 0 && ix < wd;
+        const float* px = in_n + (static_cast<size_t>(iy) * wd + ix) * 3;
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) x[(ky * 3 + kx) * 3 + ci] = ok ? __ldg(px + ci) : 0.f;
+        for (int ci = 0; ci < 3; ++ci) x[ky][j][ci] = ok ? __ldg(px + ci) : 0.f;
+      }
     }
-  }
-  __half* o = out + (static_cast<size_t>(n) * ho * wo + p) * COUT;
+    float2 acc0[kStemCh / 2], acc1[kStemCh / 2];
 #pragma unroll
-  for (int c0 = 0; c0 < COUT; c0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bs[c0 + j];
-#pragma unroll
-    for (int t = 0; t < 27; ++t) {
-      const float4 w0 = *reinterpret_cast<const float4*>(&ws[t][c0]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&ws[t][c0 + 4]);
-      acc[0] = fmaf(x[t], w0.x, acc[0]); acc[1] = fmaf(x[t], w0.y, acc[1]);
-      acc[2] = fmaf(x[t], w0.z, acc[2]); acc[3] = fmaf(x[t], w0.w, acc[3]);
-      acc[4] = fmaf(x[t], w1.x, acc[4]); acc[5] = fmaf(x[t], w1.y, acc[5]);
-      acc[6] = fmaf(x[t], w1.z, acc[6]); acc[7] = fmaf(x[t], w1.w, acc[7]);
+    for (int p = 0; p < kStemCh / 2; ++p) {
+      acc0[p] = bs[p];
+      acc1[p] = bs[p];
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = apply_act_t<ACT>(acc[j]);
-    *reinterpret_cast<uint4*>(o + c0) = float_to_half8(acc);
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const int t = (ky * 3 + kx) * 3 + ci;
+          const float2 a0 = make_float2(x[ky][kx][ci], x[ky][kx][ci]);
+          const float2 a1 = make_float2(x[ky][kx + 2][ci], x[ky][kx + 2][ci]);
+#pragma unroll
+          for (int q = 0; q < kStemCh / 4; ++q) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&ws[t][2 * q]);
+            const float2 wa = make_float2(w4.x, w4.y), wb = make_float2(w4.z, w4.w);
+            acc0[2 * q] = __ffma2_rn(a0, wa, acc0[2 * q]);
+            acc0[2 * q + 1] = __ffma2_rn(a0, wb, acc0[2 * q + 1]);
+            acc1[2 * q] = __ffma2_rn(a1, wa, acc1[2 * q]);
+            acc1[2 * q + 1] = __ffma2_rn(a1, wb, acc1[2 * q + 1]);
+          }
+        }
+      }
+    }
+    __half* o0 = out + ((static_cast<size_t>(n) * ho + oy) * wo + ox) * cout + c0;
+#pragma unroll
+    for (int g = 0; g < kStemCh / 8; ++g) {
+      if (g * 8 < cn) {
+        float f0[8], f1[8];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float2 r0 = apply_act2<ACT>(acc0[g * 4 + p]);
+          const float2 r1 = apply_act2<ACT>(acc1[g * 4 + p]);
+          f0[2 * p] = r0.x; f0[2 * p + 1] = r0.y;
+          f1[2 * p] = r1.x; f1[2 * p + 1] = r1.y;
+        }
+        *reinterpret_cast<uint4*>(o0 + g * 8) = float_to_half8(f0);
+        if (ox + 1 < wo) *reinterpret_cast<uint4*>(o0 + cout + g * 8) = float_to_half8(f1);
+      }
+    }
   }
-}
-
-template <int COUT>
-static int launch_stem(const float* in, __half* out, const __half* w, const float* bias, int n,
-                       int h, int wd, int act, cudaStream_t s) {
-  const int ho = ceil_div(h, 2), wo = ceil_div(wd, 2);
-  const int pad_t = same_pad_before(h, 3, 2), pad_l = same_pad_before(wd, 3, 2);
-  dim3 grid(ceil_div(ho * wo, kStemThreads), 1, n);
-  if (act == EDET_ACT_SWISH)
-    stem_kernel<COUT, EDET_ACT_SWISH><<<grid, kStemThreads, 0, s>>>(in, out, w, bias, h, wd, ho, wo, pad_t, pad_l);
-  else if (act == EDET_ACT_RELU6)
-    stem_kernel<COUT, EDET_ACT_RELU6><<<grid, kStemThreads, 0, s>>>(in, out, w, bias, h, wd, ho, wo, pad_t, pad_l);
-  else if (act == EDET_ACT_NONE)
-    stem_kernel<COUT, EDET_ACT_NONE><<<grid, kStemThreads, 0, s>>>(in, out, w, bias, h, wd, ho, wo, pad_t, pad_l);
-  else {
-    set_error("stem: unsupported activation %d", act);
-    return EDET_ERR_UNSUPPORTED;
-  }
-  EDET_CHECK_LAUNCH();
-  return EDET_OK;
 }
 
 }  // namespace edet
@@ -88,18 +107,25 @@ extern "C" int edet_stem_conv(const float* in, edet_half* out, const edet_half* 
   using namespace edet;
   EDET_CHECK_ARG(in && out && w && bias, "stem: null pointer");
   EDET_CHECK_ARG(n > 0 && h > 0 && wd > 0, "stem: bad shape");
+  EDET_CHECK_ARG(cout > 0 && cout % 8 == 0, "stem: cout must be a multiple of 8 (got %d)", cout);
   const __half* hw = reinterpret_cast<const __half*>(w);
-  __half* ho = reinterpret_cast<__half*>(out);
+  __half* ho_p = reinterpret_cast<__half*>(out);
   cudaStream_t s = as_stream(stream);
-  switch (cout) {
-    case 24: return launch_stem<24>(in, ho, hw, bias, n, h, wd, act, s);
-    case 32: return launch_stem<32>(in, ho, hw, bias, n, h, wd, act, s);
-    case 40: return launch_stem<40>(in, ho, hw, bias, n, h, wd, act, s);
-    case 48: return launch_stem<48>(in, ho, hw, bias, n, h, wd, act, s);
-    case 56: return launch_stem<56>(in, ho, hw, bias, n, h, wd, act, s);
-    case 64: return launch_stem<64>(in, ho, hw, bias, n, h, wd, act, s);
-    default:
-      set_error("stem: unsupported cout %d (24/32/40/48/56/64)", cout);
-      return EDET_ERR_UNSUPPORTED;
+  const int ho = ceil_div(h, 2), wo = ceil_div(wd, 2);
+  const int pad_t = same_pad_before(h, 3, 2), pad_l = same_pad_before(wd, 3, 2);
+  // ~8 pixel pairs per thread: staging the weights is amortised, yet there are enough CTAs
+  dim3 grid(ceil_div(ceil_div(ho * ((wo + 1) / 2), kStemThreads), 8), ceil_div(cout, kStemCh), n);
+  cudaError_t err = cudaSuccess;
+  if (act == EDET_ACT_SWISH)
+    err = launch_pdl(stem_kernel<EDET_ACT_SWISH>, grid, dim3(kStemThreads), 0, s, in, ho_p, hw, bias, h, wd, ho, wo, cout, pad_t, pad_l);
+  else if (act == EDET_ACT_RELU6)
+    err = launch_pdl(stem_kernel<EDET_ACT_RELU6>, grid, dim3(kStemThreads), 0, s, in, ho_p, hw, bias, h, wd, ho, wo, cout, pad_t, pad_l);
+  else if (act == EDET_ACT_NONE)
+    err = launch_pdl(stem_kernel<EDET_ACT_NONE>, grid, dim3(kStemThreads), 0, s, in, ho_p, hw, bias, h, wd, ho, wo, cout, pad_t, pad_l);
+  else {
+    set_error("stem: unsupported activation %d", act);
+    return EDET_ERR_UNSUPPORTED;
   }
+  EDET_CHECK_CUDA(err);
+  return EDET_OK;
 }
