@@ -70,6 +70,8 @@ class Engine(object):
     self._graph = None
     self._ops = []          # (name, callable)
     self.op_info = []       # parallel to _ops: kind / algorithmic bytes / flops
+    self._branch = None
+    self._branch_streams = {}
     self.buffers = {}       # debug / tests: name -> tensor
     self._keep = []         # keeps weight tensors alive
     self.launches_per_forward = 0
@@ -87,14 +89,17 @@ class Engine(object):
     self.buffers[name] = t
     return t
 
-  def _add(self, name, fn, kind='other', nbytes=0, flops=0, kernels=1):
+  def _add(self, name, fn, kind='other', nbytes=0, flops=0, kernels=1, branch=None, needs=None):
     """kind groups launches of the same kernel; nbytes / flops are the ALGORITHMIC HBM bytes
     and floating-point operations of the launch (SURVEY.md 8d formulas), used by bench.py."""
     self._ops.append((name, fn))
+    if branch is None:
+      branch = self._branch      # set while lowering independent sub-graphs (the head towers)
     self.op_info.append({'name': name, 'kind': kind, 'bytes': int(nbytes), 'flops': int(flops),
-                         'kernels': int(kernels)})
+                         'kernels': int(kernels), 'branch': branch, 'needs': list(needs or [])})
 
-  def _pw(self, name, a, wt, bias, out, act, residual=None, batch=1, rows=None, nout=None):
+  def _pw(self, name, a, wt, bias, out, act, residual=None, batch=1, rows=None, nout=None,
+          branch=None):
     if rows is None:
       rows = a.numel() // (a.shape[-1] * batch)
     impl = self.pw_impl
@@ -106,7 +111,7 @@ class Engine(object):
     self._add(name, lambda: ops.pointwise_conv(a, wt, bias, out, act, residual=residual,
                                                rows=rows, batch=batch, nout=nout, impl=impl),
               kind='pointwise_tc' if impl == ops.PW_TCGEN05 else 'pointwise_simt',
-              nbytes=nbytes, flops=2 * m * k * n_out)
+              nbytes=nbytes, flops=2 * m * k * n_out, branch=branch)
 
   # ---- network lowering -------------------------------------------------------------------
   def _build(self, w):
@@ -225,17 +230,32 @@ class Engine(object):
       wt = self._dev((kw * s).T, f16)
       bias = self._dev(cb * s + sh, f32)
       out = self._buf(r.scope + '/conv', (n, r.in_hw[0], r.in_hw[1], F))
-      self._pw(r.scope + '/conv', src, wt, bias, out, utils.ACT_NONE)
+      # a detached branch ('~' prefix): only the op that consumes `out` joins it
+      self._pw(r.scope + '/conv', src, wt, bias, out, utils.ACT_NONE, branch='~' + r.scope)
       return out
 
     pyramid = []
     for level, _ in a.pyramid_in:
       if level in feats:
         pyramid.append(feats[level])
+    # The channel-matching 1x1 convs of the backbone features (P6 creation and the first cell)
+    # only depend on the backbone: launch them all now, each on its own branch, so they overlap
+    # each other and the start of the BiFPN chain.
+    hoisted = {}
+    for r in a.extra_levels:
+      if r.has_conv:
+        hoisted[r.scope] = resample_conv(r, pyramid[r.src])
+    if a.cells:
+      for node in a.cells[0]['nodes']:
+        for r in node.inputs:
+          if r.has_conv and r.src < len(pyramid):
+            hoisted[r.scope] = resample_conv(r, pyramid[r.src])
     for r in a.extra_levels:
       src = pyramid[r.src]
+      needs = []
       if r.has_conv:
-        src = resample_conv(r, src)
+        src = hoisted[r.scope]
+        needs = ['~' + r.scope]
       if r.mode == 'same':
         # 1x1 maps cannot shrink further: the reference only applies the (optional) 1x1 conv
         # (efficientdet_arch.py:116-117), so the level aliases its source.
@@ -246,7 +266,7 @@ class Engine(object):
       out = self._buf(r.scope, (n, r.out_hw[0], r.out_hw[1], F))
       self._add(r.scope + '/pool',
                 lambda src=src, out=out, r=r: ops.max_pool(src, out, r.pool[:2], r.pool[2:]),
-                kind='max_pool', nbytes=2 * (src.numel() + out.numel()))
+                kind='max_pool', nbytes=2 * (src.numel() + out.numel()), needs=needs)
       pyramid.append(out)
 
     mode_code = {'same': ops.RS_SAME, 'up': ops.RS_UP, 'down': ops.RS_DOWN}
@@ -269,10 +289,15 @@ class Engine(object):
           fw = [1.0] * len(node.inputs)
         else:
           raise NotImplementedError('fpn_weight_method %s' % a.fpn_weight_method)
+        needs = []
         for r, wgt in zip(node.inputs, fw):
           src = cell_feats[r.src]
           if r.has_conv:
-            src = resample_conv(r, src)
+            if r.scope in hoisted:
+              src = hoisted[r.scope]
+            else:
+              src = resample_conv(r, src)
+            needs.append('~' + r.scope)
           specs.append((src, mode_code[r.mode], r.pool, float(wgt)))
         op = node.op_scope
         dw_w = self._dev(np.asarray(w[op + '/conv/depthwise_kernel'], np.float64)[..., 0].reshape(9, F), f16)
@@ -288,7 +313,7 @@ class Engine(object):
                   lambda specs=specs, dw_w=dw_w, tmp=tmp: ops.fuse_dw(specs, dw_w, tmp, act),
                   kind='bifpn_fuse_dw',
                   nbytes=2 * (sum(sp[0].numel() for sp in specs) + tmp.numel()) + 18 * F,
-                  flops=2 * 9 * tmp.numel())
+                  flops=2 * 9 * tmp.numel(), needs=needs)
         self._pw(node.scope + '/pw', tmp, pw_wt, pw_b, out, utils.ACT_NONE)
         cell_feats.append(out)
       pyramid = [cell_feats[cell['out_index'][l]] for l in a.levels]
@@ -311,6 +336,8 @@ class Engine(object):
       pred_wt = self._dev(np.asarray(w[name + '/pointwise_kernel'], np.float64)[0, 0].T, f16)  # [pred_c, F]
       pred_b = self._dev(w[name + '/bias'], f32)
       for level in a.levels:
+        # every (tower, level) chain is independent: it becomes a parallel branch of the graph
+        self._branch = '%s/l%d' % (scope, level)
         hh, ww = a.level_hw[level]
         x = self.fpn_feats[level]
         t = self._buf('%s/l%d/t' % (scope, level), (n, hh, ww, F))
@@ -334,6 +361,7 @@ class Engine(object):
         self._pw('%s/l%d/predict' % (scope, level), t, pred_wt, pred_b, out, utils.ACT_NONE,
                  nout=pred_c)
         (self.cls_out if net == 'class' else self.box_out)[level] = out
+    self._branch = None
     self.num_network_ops = len(self._ops)
 
     # -- post-processing ----------------------------------------------------------------------
@@ -385,9 +413,33 @@ class Engine(object):
     self.launches_per_forward = sum(i['kernels'] for i in self.op_info)
 
   # ---- execution ------------------------------------------------------------------------------
-  def _run_ops(self, upto=None):
-    for _, fn in (self._ops if upto is None else self._ops[:upto]):
-      fn()
+  def _run_ops(self, upto=None, parallel_branches=True):
+    """Runs the launch list on the current stream; ops tagged with a branch run on side streams
+    forked from / joined back into it (parallel graph branches when captured)."""
+    ops_list = self._ops if upto is None else self._ops[:upto]
+    main = torch.cuda.current_stream(self.device)
+    open_branches = {}
+    for i, (_, fn) in enumerate(ops_list):
+      br = self.op_info[i]['branch'] if parallel_branches else None
+      if br is None:
+        # join every open branch except the detached ('~...') ones this op does not consume
+        needs = self.op_info[i]['needs']
+        for name in list(open_branches):
+          if not name.startswith('~') or name in needs:
+            main.wait_stream(open_branches.pop(name))
+        fn()
+        continue
+      st = open_branches.get(br)
+      if st is None:
+        st = self._branch_streams.get(br)
+        if st is None:
+          st = self._branch_streams[br] = torch.cuda.Stream(device=self.device)
+        st.wait_stream(main)                   # fork
+        open_branches[br] = st
+      with torch.cuda.stream(st):
+        fn()
+    for st in open_branches.values():
+      main.wait_stream(st)
 
   # buffers of the most recent post-processed step
   @property
@@ -513,7 +565,7 @@ class Engine(object):
     (eager launches, not the graph) and returns op_info rows extended with 'ms' (mean)."""
     upto = len(self._ops) if postprocess else self.num_network_ops
     with torch.cuda.device(self.device):
-      self._run_ops(upto)  # warm-up
+      self._run_ops(upto, parallel_branches=False)  # warm-up
       torch.cuda.synchronize()
       acc = [0.0] * upto
       for _ in range(iters):
