@@ -38,6 +38,9 @@ SIGNATURES = {
                                     c_void_p]),
     'edet_depthwise_conv': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'edet_mbconv_expand_dw': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_void_p]),
     'edet_se_fc': (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                            c_int, c_void_p]),

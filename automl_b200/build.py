@@ -22,7 +22,8 @@ def _sources():
 def _digest():
   h = hashlib.sha256()
   inc = os.path.join(os.path.dirname(os.path.dirname(CSRC)), 'include', 'automl_b200.h')
-  for f in _sources() + [os.path.join(CSRC, 'common.cuh'), inc]:
+  headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh'))
+  for f in _sources() + headers + [inc]:
     with open(f, 'rb') as fh:
       h.update(f.encode())
       h.update(fh.read())

@@ -75,6 +75,17 @@ def depthwise_conv(x, out, w, bias, act, k, stride, se_sum=None):
             n, h, wd, c, k, stride, act, _stream())
 
 
+def mbconv_expand_dw(x, we, bias_e, wd, bias_d, out, act, k, stride, se_sum=None):
+  """Fused expand 1x1 + depthwise kxk: x fp16 [N,H,W,cin], we fp16 [cmid,cin], wd fp16
+  [k*k,cmid], out fp16 [N,Ho,Wo,cmid]; se_sum int64 [N,cmid] (added to) or None."""
+  n, h, wd_, cin = x.shape
+  cmid = we.shape[0]
+  _lib.call('edet_mbconv_expand_dw', _ptr(x, torch.float16), _ptr(we, torch.float16),
+            _ptr(bias_e, torch.float32), _ptr(wd, torch.float16), _ptr(bias_d, torch.float32),
+            _ptr(out, torch.float16), _ptr(se_sum, torch.int64), n, h, wd_, cin, cmid, k, stride,
+            act, _stream())
+
+
 def se_fc(se_sum, inv_hw, w1, b1, w2, b2, gate, act, wt=None, wt_scaled=None, zero_buf=None):
   """se_sum int64 [N, C]; zero_buf: int64 [N, Cz] buffer cleared by the same launch."""
   n, c = gate.shape

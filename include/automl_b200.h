@@ -81,6 +81,21 @@ int edet_preprocess(const uint8_t* in, float* out, int n, int h, int w, int out_
 int edet_stem_conv(const float* in, edet_half* out, const edet_half* w, const float* bias,
                    int n, int h, int wd, int cout, int act, edet_stream_t stream);
 
+/* Fused front half of an MBConv block: expand 1x1 + BN + act  ->  depthwise kxk 'SAME' + BN +
+ * act (+ SE squeeze), the expanded [N,H,W,cmid] tensor never leaves the SM (tcgen05 accumulators
+ * in TMEM -> fp16 tile in shared memory -> depthwise).  Same results as edet_pointwise_conv
+ * followed by edet_depthwise_conv (the expanded value is rounded to fp16 in both).
+ * Replaces: backbone/efficientnet_model.py:303-333 (the two convs + BNs), :387-391 (their use in
+ * MBConvBlock._call) and the reduce_mean of :192.
+ *   x [n,h,w,cin] fp16 (cin % 8 == 0), we [cmid][cin] fp16, bias_e [cmid] f32,
+ *   wd [k*k][cmid] fp16, bias_d [cmid] f32, out [n,ceil(h/stride),ceil(w/stride),cmid] fp16,
+ *   se_sum int64 [n][cmid] (2^-20 fixed point, ADDED to) or NULL; k in {3,5}, stride in {1,2},
+ *   act in {EDET_ACT_SWISH, EDET_ACT_RELU6} applied after both convs (as the reference does). */
+int edet_mbconv_expand_dw(const edet_half* x, const edet_half* we, const float* bias_e,
+                          const edet_half* wd, const float* bias_d, edet_half* out,
+                          int64_t* se_sum, int n, int h, int w, int cin, int cmid, int k,
+                          int stride, int act, edet_stream_t stream);
+
 /*
  * Pointwise (1x1) convolution as a GEMM with fused epilogue:
  *   out[b, r, :] = act( A[b, r, :] @ Wt[b or 0]^T + bias ) (+ residual[b, r, :])

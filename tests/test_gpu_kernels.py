@@ -129,6 +129,50 @@ def test_depthwise_conv(case):
     assert torch.equal(again, partial)
 
 
+# n, h, w, cin, cmid, k, stride, act, has_se   (D0 blocks 1-5 shapes at small sizes + edge cases)
+MBF_CASES = [
+    (2, 40, 40, 16, 96, 3, 2, utils.ACT_SWISH, True),     # block 1: one chunk, 32B swizzle
+    (2, 33, 29, 24, 144, 3, 1, utils.ACT_SWISH, True),    # block 2: two chunks (80 + 64), K pad 24 -> 32
+    (1, 37, 41, 24, 144, 5, 2, utils.ACT_SWISH, True),    # block 3
+    (2, 20, 20, 40, 240, 5, 1, utils.ACT_SWISH, True),    # block 4: two k-blocks of 32
+    (1, 23, 17, 40, 240, 3, 2, utils.ACT_RELU6, False),   # block 5 (lite flavour)
+    (1, 16, 16, 80, 480, 3, 1, utils.ACT_SWISH, True),    # 4 chunks, 128B swizzle, two k-blocks
+    (1, 5, 7, 16, 96, 5, 1, utils.ACT_SWISH, True),       # image smaller than one patch
+    (3, 64, 64, 16, 96, 3, 2, utils.ACT_SWISH, True),     # several full tiles per image
+]
+
+
+@pytest.mark.parametrize('case', MBF_CASES)
+def test_mbconv_expand_dw(case):
+  ops = _ops()
+  n, h, w, cin, cmid, k, s, act, has_se = case
+  g = torch.Generator().manual_seed(7 + h + cmid + k)
+  x = torch.randn(n, h, w, cin, generator=g).half()
+  we = (torch.randn(cmid, cin, generator=g) / cin**0.5).half()
+  be = torch.randn(cmid, generator=g) * 0.2
+  wk = (torch.randn(k, k, cmid, generator=g) / k).half()
+  bd = torch.randn(cmid, generator=g) * 0.1
+  ho, wo = -(-h // s), -(-w // s)
+  out = torch.full((n, ho, wo, cmid), 7.0, dtype=torch.float16, device=DEV)
+  se = torch.zeros(n, cmid, dtype=torch.int64, device=DEV) if has_se else None
+  args = (x.to(DEV), we.to(DEV), be.to(DEV), wk.reshape(k * k, cmid).to(DEV), bd.to(DEV))
+  ops.mbconv_expand_dw(*args, out, act, k, s, se)
+  torch.cuda.synchronize()
+  # reference: the expanded map is an fp16 tensor (as in the unfused pipeline)
+  e = act_ref(x.double() @ we.double().t() + be.double(), act).half().double()
+  ref = eo.depthwise_conv2d_same(e.permute(0, 3, 1, 2), wk.double().unsqueeze(-1), s)
+  ref = act_ref(ref + bd.double().view(1, -1, 1, 1), act).permute(0, 2, 3, 1)
+  got = out.cpu().double()
+  assert torch.allclose(got, ref, rtol=2e-3, atol=2e-3), float((got - ref).abs().max())
+  if has_se:
+    sums = se.cpu().double() / 2.0**20
+    np.testing.assert_allclose(sums.numpy(), ref.sum((1, 2)).numpy(), rtol=1e-3, atol=0.05)
+    again = torch.zeros_like(se)
+    ops.mbconv_expand_dw(*args, out, act, k, s, again)
+    torch.cuda.synchronize()
+    assert torch.equal(again, se)
+
+
 def test_se_fc():
   ops = _ops()
   n, c, se, nout = 3, 96, 4, 24
