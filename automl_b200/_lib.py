@@ -42,10 +42,12 @@ SIGNATURES = {
                                       c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_void_p]),
     'edet_se_fc': (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                           c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                           c_int, c_void_p]),
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                           c_int, c_int, c_void_p]),
     'edet_fuse_dw': (c_int, [ctypes.POINTER(FuseInput), c_int, c_void_p, c_void_p, c_int, c_int,
                              c_int, c_int, c_int, c_void_p]),
+    'edet_sepconv': (c_int, [ctypes.POINTER(FuseInput), c_int, c_int, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'edet_max_pool': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_int, c_int, c_void_p]),
     'edet_pre_nms': (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),

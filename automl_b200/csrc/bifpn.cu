@@ -4,35 +4,13 @@
 // used to create the extra P6.. levels.
 //
 // Memory-bound: bytes = 2*n*c*(sum_inputs h_i*w_i + h*w) + 2*9*c.
-#include <math_constants.h>
-
-#include "common.cuh"
+#include "fuse_common.cuh"
 
 namespace edet {
 
 constexpr int kFuseThreads = 256;
 constexpr int kFuseTH = 8, kFuseTW = 16;   // output tile
 constexpr int kFuseCB = 32;                // channels per CTA
-constexpr int kFuseMaxIn = 3;
-
-struct FuseIn {
-  const __half* ptr;
-  int h, w, mode;
-  int pool_h, pool_w, stride_h, stride_w, pad_t, pad_l;
-  float scale_h, scale_w;  // in/out, float32 as TF computes it
-  float weight;
-};
-struct FuseParams {
-  FuseIn in[kFuseMaxIn];
-  int n_inputs;
-};
-
-__device__ __forceinline__ void load8(const __half* base, int hh, int ww, int c, int y, int x,
-                                      int ch, float* f) {
-  half8_to_float(__ldg(reinterpret_cast<const uint4*>(
-                     base + (static_cast<size_t>(y) * ww + x) * c + ch)), f);
-}
-
 template <int ACT>
 __global__ void __launch_bounds__(kFuseThreads)
 fuse_dw_kernel(const FuseParams p, const __half* __restrict__ dw_w, __half* __restrict__ out,
@@ -60,34 +38,16 @@ fuse_dw_kernel(const FuseParams p, const __half* __restrict__ dw_w, __half* __re
         const FuseIn& fi = p.in[i];
         const __half* base = fi.ptr + static_cast<size_t>(n) * fi.h * fi.w * c;
         float v[8];
-        if (fi.mode == EDET_RS_SAME) {
-          load8(base, fi.h, fi.w, c, y, x, ch, v);
-        } else if (fi.mode == EDET_RS_UP) {
-          const int sy = min(static_cast<int>(floorf(__fmul_rn(static_cast<float>(y), fi.scale_h))), fi.h - 1);
-          const int sx = min(static_cast<int>(floorf(__fmul_rn(static_cast<float>(x), fi.scale_w))), fi.w - 1);
-          load8(base, fi.h, fi.w, c, sy, sx, ch, v);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = -CUDART_INF_F;
-          const int sy0 = y * fi.stride_h - fi.pad_t, sx0 = x * fi.stride_w - fi.pad_l;
-          for (int py = 0; py < fi.pool_h; ++py) {
-            const int sy = sy0 + py;
-            if (sy < 0 || sy >= fi.h) continue;
-            for (int px = 0; px < fi.pool_w; ++px) {
-              const int sx = sx0 + px;
-              if (sx < 0 || sx >= fi.w) continue;
-              float t[8];
-              load8(base, fi.h, fi.w, c, sy, sx, ch, t);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], t[e]);
-            }
-          }
-        }
+        resample8(fi, base, c, y, x, ch, v);
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], fi.weight, acc[e]);
       }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = apply_act_t<ACT>(acc[e]);
+      for (int e = 0; e < 8; e += 4) {
+        float2 a = make_float2(acc[e], acc[e + 1]), b = make_float2(acc[e + 2], acc[e + 3]);
+        apply_act4<ACT>(a, b);
+        acc[e] = a.x; acc[e + 1] = a.y; acc[e + 2] = b.x; acc[e + 3] = b.y;
+      }
     }
     float4* dst = reinterpret_cast<float4*>(&fused[pix][g * 8]);
     dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -165,36 +125,10 @@ extern "C" int edet_fuse_dw(const edet_fuse_input* h_inputs, int n_inputs, const
                             edet_half* out, int n, int h, int wd, int c, int act,
                             edet_stream_t stream) {
   using namespace edet;
-  EDET_CHECK_ARG(h_inputs && dw_w && out, "fuse_dw: null pointer");
-  EDET_CHECK_ARG(n_inputs >= 1 && n_inputs <= kFuseMaxIn, "fuse_dw: 1..3 inputs (got %d)", n_inputs);
+  EDET_CHECK_ARG(dw_w && out, "fuse_dw: null pointer");
   EDET_CHECK_ARG(n > 0 && h > 0 && wd > 0 && c > 0 && c % 8 == 0, "fuse_dw: bad shape");
   FuseParams p;
-  p.n_inputs = n_inputs;
-  for (int i = 0; i < n_inputs; ++i) {
-    const edet_fuse_input& s = h_inputs[i];
-    FuseIn& d = p.in[i];
-    EDET_CHECK_ARG(s.ptr != nullptr, "fuse_dw: input %d is null", i);
-    d.ptr = reinterpret_cast<const __half*>(s.ptr);
-    d.h = s.h; d.w = s.w; d.mode = s.mode; d.weight = s.weight;
-    d.pool_h = d.pool_w = d.stride_h = d.stride_w = 1; d.pad_t = d.pad_l = 0;
-    d.scale_h = d.scale_w = 1.f;
-    if (s.mode == EDET_RS_SAME) {
-      EDET_CHECK_ARG(s.h == h && s.w == wd, "fuse_dw: input %d is %dx%d, node is %dx%d", i, s.h, s.w, h, wd);
-    } else if (s.mode == EDET_RS_UP) {
-      EDET_CHECK_ARG(s.h <= h && s.w <= wd, "fuse_dw: input %d cannot be upsampled", i);
-      d.scale_h = static_cast<float>(s.h) / static_cast<float>(h);
-      d.scale_w = static_cast<float>(s.w) / static_cast<float>(wd);
-    } else if (s.mode == EDET_RS_DOWN) {
-      EDET_CHECK_ARG(ceil_div(s.h, s.stride_h) == h && ceil_div(s.w, s.stride_w) == wd,
-                     "fuse_dw: input %d pooled size mismatch", i);
-      d.pool_h = s.pool_h; d.pool_w = s.pool_w; d.stride_h = s.stride_h; d.stride_w = s.stride_w;
-      d.pad_t = same_pad_before(s.h, s.pool_h, s.stride_h);
-      d.pad_l = same_pad_before(s.w, s.pool_w, s.stride_w);
-    } else {
-      set_error("fuse_dw: bad mode %d", s.mode);
-      return EDET_ERR_INVALID;
-    }
-  }
+  if (int rc = fill_fuse_params(h_inputs, n_inputs, h, wd, "fuse_dw", &p)) return rc;
   const int chunks = ceil_div(c, kFuseCB);
   dim3 grid(ceil_div(wd, kFuseTW), ceil_div(h, kFuseTH), n * chunks);
   const __half* hw = reinterpret_cast<const __half*>(dw_w);

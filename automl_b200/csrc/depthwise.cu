@@ -144,12 +144,17 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       if (interior || oy0 + r < ho) {
+        float2 o[TW];
+#pragma unroll
+        for (int tx = 0; tx < TW; ++tx) o[tx] = __fadd2_rn(acc[r][tx], bv);
+#pragma unroll
+        for (int tx = 0; tx + 1 < TW; tx += 2) apply_act4<ACT>(o[tx], o[tx + 1]);
+        if (TW & 1) o[TW - 1] = apply_act2<ACT>(o[TW - 1]);
 #pragma unroll
         for (int tx = 0; tx < TW; ++tx) {
           if (interior || ox0 + tx < wo) {
-            const float2 o = apply_act2<ACT>(__fadd2_rn(acc[r][tx], bv));
-            if (HAS_SE) ssum = __fadd2_rn(ssum, o);
-            orow[tx * cp_count] = __floats2half2_rn(o.x, o.y);
+            if (HAS_SE) ssum = __fadd2_rn(ssum, o[tx]);
+            orow[tx * cp_count] = __floats2half2_rn(o[tx].x, o[tx].y);
           }
         }
       }
@@ -183,89 +188,106 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
   }
 }
 
-// SE gate: one CTA per image.
-//   mean[c] = inv_hw * se_sum[n][c] / 2^20
-//   r[j]    = act(b1[j] + sum_c w1[j][c] * mean[c])
-//   gate[c] = sigmoid(b2[c] + sum_j w2t[j][c] * r[j])
-// and clears `zero_buf` (the squeeze accumulator the NEXT block will use).
-__global__ void __launch_bounds__(512)
-se_gate_kernel(const long long* __restrict__ se_sum, float inv_hw, const float* __restrict__ w1,
-               const float* __restrict__ b1, const float* __restrict__ w2t,
-               const float* __restrict__ b2, float* __restrict__ gate,
-               long long* __restrict__ zero_buf, int zero_count, int c, int se, int act) {
+// SE, first FC: one WARP per (image, squeezed unit), so the n * se dot products of length c run
+// on n * se / 8 CTAs with every load of a lane independent (pure latency otherwise).
+//   mean[c]      = inv_hw * se_sum[n][c] / 2^20
+//   hidden[n][j] = act(b1[j] + sum_c w1[j][c] * mean[c])
+// Also clears `zero_buf` (the squeeze accumulator the NEXT block will use).
+constexpr int kSeWarps = 8;
+__global__ void __launch_bounds__(kSeWarps * 32)
+se_fc1_kernel(const long long* __restrict__ se_sum, float inv_hw, const float* __restrict__ w1,
+              const float* __restrict__ b1, float* __restrict__ hidden,
+              long long* __restrict__ zero_buf, long long zero_total, int n, int c, int se, int act) {
+  pdl_launch_dependents();
+  pdl_wait_prior();
+  if (zero_buf != nullptr) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < zero_total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+      zero_buf[i] = 0;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * kSeWarps + warp;
+  if (unit >= n * se) return;
+  const int img = unit / se, j = unit - img * se;
+  const long long* sums = se_sum + static_cast<size_t>(img) * c;
+  const float* wr = w1 + static_cast<size_t>(j) * c;
+  const double scale = (1.0 / kSeFixedScale) * static_cast<double>(inv_hw);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int ch = lane;
+  for (; ch + 96 < c; ch += 128) {
+    const long long q0 = sums[ch], q1 = sums[ch + 32], q2 = sums[ch + 64], q3 = sums[ch + 96];
+    const float a0 = __ldg(wr + ch), a1 = __ldg(wr + ch + 32), a2 = __ldg(wr + ch + 64),
+                a3 = __ldg(wr + ch + 96);
+    s0 = fmaf(a0, static_cast<float>(static_cast<double>(q0) * scale), s0);
+    s1 = fmaf(a1, static_cast<float>(static_cast<double>(q1) * scale), s1);
+    s2 = fmaf(a2, static_cast<float>(static_cast<double>(q2) * scale), s2);
+    s3 = fmaf(a3, static_cast<float>(static_cast<double>(q3) * scale), s3);
+  }
+  for (; ch < c; ch += 32)
+    s0 = fmaf(__ldg(wr + ch), static_cast<float>(static_cast<double>(sums[ch]) * scale), s0);
+  float s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) hidden[static_cast<size_t>(img) * se + j] = apply_act(s + b1[j], act);
+}
+
+// SE, second FC + excitation folded into the project weights, one CTA per (128-channel slice,
+// image):
+//   gate[n][c]            = sigmoid(b2[c] + sum_j w2t[j][c] * hidden[n][j])
+//   wt_scaled[n][o][c]    = wt[o][c] * gate[n][c]
+constexpr int kSeSlice = 128;
+__global__ void __launch_bounds__(256)
+se_fc2_scale_kernel(const float* __restrict__ hidden, const float* __restrict__ w2t,
+                    const float* __restrict__ b2, float* __restrict__ gate,
+                    const __half* __restrict__ wt, __half* __restrict__ wt_scaled, int c, int se,
+                    int nout) {
   pdl_launch_dependents();
   pdl_wait_prior();
   extern __shared__ float sm[];
-  float* mean = sm;        // [c]
-  float* red = sm + c;     // [se]
-  const int n = blockIdx.x;
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x)
-    mean[ch] = static_cast<float>(static_cast<double>(se_sum[static_cast<size_t>(n) * c + ch]) *
-                                  (1.0 / kSeFixedScale) * static_cast<double>(inv_hw));
-  if (zero_buf != nullptr) {
-    for (int i = threadIdx.x; i < zero_count; i += blockDim.x)
-      zero_buf[static_cast<size_t>(n) * zero_count + i] = 0;
+  float* hid = sm;              // [se]
+  float* g = sm + ((se + 3) & ~3);   // [kSeSlice], 16-byte aligned
+  const int n = blockIdx.y, c0 = blockIdx.x * kSeSlice;
+  for (int j = threadIdx.x; j < se; j += blockDim.x) hid[j] = hidden[static_cast<size_t>(n) * se + j];
+  __syncthreads();
+  if (threadIdx.x < kSeSlice) {
+    const int ch = c0 + threadIdx.x;
+    float v = 0.f;
+    if (ch < c) {
+      float s0 = b2[ch], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int j = 0;
+      for (; j + 3 < se; j += 4) {
+        const float a0 = __ldg(w2t + static_cast<size_t>(j) * c + ch);
+        const float a1 = __ldg(w2t + static_cast<size_t>(j + 1) * c + ch);
+        const float a2 = __ldg(w2t + static_cast<size_t>(j + 2) * c + ch);
+        const float a3 = __ldg(w2t + static_cast<size_t>(j + 3) * c + ch);
+        s0 = fmaf(a0, hid[j], s0);
+        s1 = fmaf(a1, hid[j + 1], s1);
+        s2 = fmaf(a2, hid[j + 2], s2);
+        s3 = fmaf(a3, hid[j + 3], s3);
+      }
+      for (; j < se; ++j) s0 = fmaf(__ldg(w2t + static_cast<size_t>(j) * c + ch), hid[j], s0);
+      v = 1.0f / (1.0f + expf(-((s0 + s1) + (s2 + s3))));
+      gate[static_cast<size_t>(n) * c + ch] = v;
+    }
+    g[threadIdx.x] = v;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  // Both FCs are pure latency (a few thousand MACs): keep 4-8 independent loads in flight.
-  for (int j = warp; j < se; j += nwarps) {
-    const float* wr = w1 + static_cast<size_t>(j) * c;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int ch = lane;
-    for (; ch + 96 < c; ch += 128) {
-      const float a0 = __ldg(wr + ch), a1 = __ldg(wr + ch + 32), a2 = __ldg(wr + ch + 64),
-                  a3 = __ldg(wr + ch + 96);
-      s0 = fmaf(a0, mean[ch], s0);
-      s1 = fmaf(a1, mean[ch + 32], s1);
-      s2 = fmaf(a2, mean[ch + 64], s2);
-      s3 = fmaf(a3, mean[ch + 96], s3);
-    }
-    for (; ch < c; ch += 32) s0 = fmaf(__ldg(wr + ch), mean[ch], s0);
-    float s = (s0 + s1) + (s2 + s3);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) red[j] = apply_act(s + b1[j], act);
+  if (wt == nullptr) return;
+  // 16 x 16-byte pieces per 128-channel row slice; 256 threads cover 16 rows per pass
+  const int piece = threadIdx.x & 15, row0 = threadIdx.x >> 4;
+  const int ch = c0 + piece * 8;
+  if (ch >= c) return;
+  const float4 g0 = *reinterpret_cast<const float4*>(g + piece * 8);
+  const float4 g1 = *reinterpret_cast<const float4*>(g + piece * 8 + 4);
+  __half* dst = wt_scaled + static_cast<size_t>(n) * nout * c;
+#pragma unroll 4
+  for (int o = row0; o < nout; o += 16) {
+    float f[8];
+    half8_to_float(__ldg(reinterpret_cast<const uint4*>(wt + static_cast<size_t>(o) * c + ch)), f);
+    f[0] *= g0.x; f[1] *= g0.y; f[2] *= g0.z; f[3] *= g0.w;
+    f[4] *= g1.x; f[5] *= g1.y; f[6] *= g1.z; f[7] *= g1.w;
+    *reinterpret_cast<uint4*>(dst + static_cast<size_t>(o) * c + ch) = float_to_half8(f);
   }
-  __syncthreads();
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    float s0 = b2[ch], s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int j = 0;
-    for (; j + 3 < se; j += 4) {
-      const float a0 = __ldg(w2t + static_cast<size_t>(j) * c + ch);
-      const float a1 = __ldg(w2t + static_cast<size_t>(j + 1) * c + ch);
-      const float a2 = __ldg(w2t + static_cast<size_t>(j + 2) * c + ch);
-      const float a3 = __ldg(w2t + static_cast<size_t>(j + 3) * c + ch);
-      s0 = fmaf(a0, red[j], s0);
-      s1 = fmaf(a1, red[j + 1], s1);
-      s2 = fmaf(a2, red[j + 2], s2);
-      s3 = fmaf(a3, red[j + 3], s3);
-    }
-    for (; j < se; ++j) s0 = fmaf(__ldg(w2t + static_cast<size_t>(j) * c + ch), red[j], s0);
-    const float s = (s0 + s1) + (s2 + s3);
-    gate[static_cast<size_t>(n) * c + ch] = 1.0f / (1.0f + expf(-s));
-  }
-}
-
-// Excitation folded into the project weights: wt_scaled[n][o][c] = wt[o][c] * gate[n][c].
-__global__ void __launch_bounds__(256)
-se_scale_kernel(const float* __restrict__ gate, const __half* __restrict__ wt,
-                __half* __restrict__ wt_scaled, int c, int nout) {
-  pdl_launch_dependents();
-  pdl_wait_prior();
-  const int n = blockIdx.y;
-  const int cg = c >> 3;
-  const int total = nout * cg;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int gidx = i % cg;
-  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(n) * c) + gidx * 2);
-  const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(n) * c) + gidx * 2 + 1);
-  float f[8];
-  half8_to_float(__ldg(reinterpret_cast<const uint4*>(wt) + i), f);
-  f[0] *= g0.x; f[1] *= g0.y; f[2] *= g0.z; f[3] *= g0.w;
-  f[4] *= g1.x; f[5] *= g1.y; f[6] *= g1.z; f[7] *= g1.w;
-  reinterpret_cast<uint4*>(wt_scaled + static_cast<size_t>(n) * nout * c)[i] = float_to_half8(f);
 }
 
 template <int K, int S>
@@ -316,25 +338,24 @@ extern "C" int edet_depthwise_conv(const edet_half* in, edet_half* out, const ed
 }
 
 extern "C" int edet_se_fc(const int64_t* se_sum, float inv_hw, const float* w1, const float* b1,
-                          const float* w2, const float* b2, float* gate, const edet_half* wt,
-                          edet_half* wt_scaled, int64_t* zero_buf, int zero_count, int n, int c,
-                          int se, int nout, int act, edet_stream_t stream) {
+                          const float* w2, const float* b2, float* hidden, float* gate,
+                          const edet_half* wt, edet_half* wt_scaled, int64_t* zero_buf,
+                          int zero_count, int n, int c, int se, int nout, int act,
+                          edet_stream_t stream) {
   using namespace edet;
-  EDET_CHECK_ARG(se_sum && w1 && b1 && w2 && b2 && gate, "se_fc: null pointer");
+  EDET_CHECK_ARG(se_sum && w1 && b1 && w2 && b2 && hidden && gate, "se_fc: null pointer");
   EDET_CHECK_ARG(n > 0 && c > 0 && c % 8 == 0 && se > 0, "se_fc: bad shape");
   EDET_CHECK_ARG(!wt || (wt_scaled && nout > 0), "se_fc: wt given without wt_scaled/nout");
-  const size_t smem = static_cast<size_t>(c + se) * sizeof(float);
-  EDET_CHECK_ARG(smem <= 48 * 1024, "se_fc: c too large");
-  EDET_CHECK_CUDA(launch_pdl(se_gate_kernel, dim3(n), dim3(512), smem, as_stream(stream),
-                             reinterpret_cast<const long long*>(se_sum), inv_hw, w1, b1, w2, b2, gate,
-                             reinterpret_cast<long long*>(zero_buf), zero_count, c, se, act));
-  if (wt) {
-    const int total = nout * (c >> 3);
-    EDET_CHECK_CUDA(launch_pdl(se_scale_kernel, dim3(ceil_div(total, 256), n), dim3(256), 0,
-                               as_stream(stream), static_cast<const float*>(gate),
-                               reinterpret_cast<const __half*>(wt),
-                               reinterpret_cast<__half*>(wt_scaled), c, nout));
-  }
+  const size_t smem = static_cast<size_t>(((se + 3) & ~3) + kSeSlice) * sizeof(float);
+  EDET_CHECK_ARG(smem <= 48 * 1024, "se_fc: se too large");
+  EDET_CHECK_CUDA(launch_pdl(se_fc1_kernel, dim3(ceil_div(n * se, kSeWarps)), dim3(kSeWarps * 32),
+                             0, as_stream(stream), reinterpret_cast<const long long*>(se_sum),
+                             inv_hw, w1, b1, hidden, reinterpret_cast<long long*>(zero_buf),
+                             static_cast<long long>(n) * zero_count, n, c, se, act));
+  EDET_CHECK_CUDA(launch_pdl(se_fc2_scale_kernel, dim3(ceil_div(c, kSeSlice), n), dim3(256), smem,
+                             as_stream(stream), static_cast<const float*>(hidden), w2, b2, gate,
+                             reinterpret_cast<const __half*>(wt),
+                             reinterpret_cast<__half*>(wt_scaled), c, se, nout));
   EDET_CHECK_LAUNCH();
   return EDET_OK;
 }

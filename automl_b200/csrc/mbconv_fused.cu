@@ -29,6 +29,24 @@ using namespace pwtc;
 constexpr int kThreads = 256;
 constexpr int kPatch = 16;                 // input patch is kPatch x kPatch pixels
 constexpr int kPatchPx = kPatch * kPatch;  // 256 rows of the expand GEMM
+constexpr int kMaxCh = 128;                // expanded channels per tile (2 x 128 TMEM columns)
+// bytes per pixel row of the smem E tile: (pitch / 16) odd -> conflict-free 128-bit row writes;
+// a compile-time constant so that every depthwise tap is an immediate offset
+constexpr int kEPitch = kMaxCh * 2 + 16;
+
+__device__ __forceinline__ uint32_t lds_b32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float2 h2_bits_to_f2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
 
 struct Params {
   int n, h, w, cin, cmid, ho, wo, pad_t, pad_l;
@@ -36,7 +54,6 @@ struct Params {
   int ch, num_chunks;          // expanded channels per CTA tile, number of chunks
   int oth, otw;                // output tile (rows, cols) produced from one input patch
   int tiles_y, tiles_x, total_tiles;
-  int e_pitch;                 // bytes per pixel row of the smem E tile
   int tmem_cols;
   const float* bias_e;         // [cmid]
   const __half* wd;            // [k*k][cmid]
@@ -73,7 +90,7 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
   uint8_t* smem_b = smem_a + p.a_bytes;         // [ch][block_k] swizzled
   uint8_t* smem_e = smem_b + p.b_bytes;         // [256 px][e_pitch] fp16
   unsigned long long* se_s =
-      reinterpret_cast<unsigned long long*>(smem_e + kPatchPx * p.e_pitch);  // [ch]
+      reinterpret_cast<unsigned long long*>(smem_e + kPatchPx * kEPitch);  // [ch]
   uint64_t* bars = reinterpret_cast<uint64_t*>(se_s + p.ch);
   const uint32_t full_bar = smem_u32(bars);       // TMA -> MMA            (thread 0 only)
   const uint32_t kb_bar = smem_u32(bars + 1);     // MMA k-block retired   (thread 0 only)
@@ -164,7 +181,7 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
       const int py = m / kPatch, px = m % kPatch;
       const int iy = tl.ty * OTW * S - p.pad_t + py, ix = tl.tx * OTW * S - p.pad_l + px;
       const bool inside = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
-      uint8_t* erow = smem_e + m * p.e_pitch;
+      const uint32_t erow = smem_u32(smem_e) + m * kEPitch;
       const float* be = p.bias_e + cbase;
       for (int c0 = 0; c0 < cv; c0 += 16) {
         float v[16];
@@ -174,21 +191,20 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (c0 + g * 8 < cv) {
-            float o[8];
+            uint4 packed = make_uint4(0u, 0u, 0u, 0u);   // TF zero-pads the EXPANDED map
             if (inside) {
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(be + c0 + g * 8));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(be + c0 + g * 8 + 4));
-              const float2 r0 = apply_act2<ACT>(__fadd2_rn(make_float2(v[g * 8 + 0], v[g * 8 + 1]), make_float2(b0.x, b0.y)));
-              const float2 r1 = apply_act2<ACT>(__fadd2_rn(make_float2(v[g * 8 + 2], v[g * 8 + 3]), make_float2(b0.z, b0.w)));
-              const float2 r2 = apply_act2<ACT>(__fadd2_rn(make_float2(v[g * 8 + 4], v[g * 8 + 5]), make_float2(b1.x, b1.y)));
-              const float2 r3 = apply_act2<ACT>(__fadd2_rn(make_float2(v[g * 8 + 6], v[g * 8 + 7]), make_float2(b1.z, b1.w)));
-              o[0] = r0.x; o[1] = r0.y; o[2] = r1.x; o[3] = r1.y;
-              o[4] = r2.x; o[5] = r2.y; o[6] = r3.x; o[7] = r3.y;
-            } else {   // TF zero-pads the EXPANDED map, not the input
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = 0.f;
+              float2 r0 = __fadd2_rn(make_float2(v[g * 8 + 0], v[g * 8 + 1]), make_float2(b0.x, b0.y));
+              float2 r1 = __fadd2_rn(make_float2(v[g * 8 + 2], v[g * 8 + 3]), make_float2(b0.z, b0.w));
+              float2 r2 = __fadd2_rn(make_float2(v[g * 8 + 4], v[g * 8 + 5]), make_float2(b1.x, b1.y));
+              float2 r3 = __fadd2_rn(make_float2(v[g * 8 + 6], v[g * 8 + 7]), make_float2(b1.z, b1.w));
+              apply_act4<ACT>(r0, r1);
+              apply_act4<ACT>(r2, r3);
+              const float o[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};
+              packed = float_to_half8(o);
             }
-            *reinterpret_cast<uint4*>(erow + (c0 + g * 8) * 2) = float_to_half8(o);
+            sts_v4(erow + (c0 + g * 8) * 2, packed);
           }
         }
       }
@@ -203,10 +219,11 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
       const int oy0 = tl.ty * OTW, ox0 = tl.tx * OTW;
       const int rows = min(OTW, p.ho - oy0), cols = min(OTW, p.wo - ox0);
       const int cm2 = p.cmid >> 1;
+      const uint32_t e_u32 = smem_u32(smem_e);
       for (int item = threadIdx.x; item < rows * cpn; item += kThreads) {
         const int oyl = item / cpn, cp = item - oyl * cpn;
         const __half2* wd2 = reinterpret_cast<const __half2*>(p.wd) + ((cbase >> 1) + cp);
-        const uint8_t* ebase = smem_e + (oyl * S * kPatch) * p.e_pitch + cp * 4;
+        const uint32_t ebase = e_u32 + (oyl * S * kPatch) * kEPitch + cp * 4;
         float2 acc[OTW];
 #pragma unroll
         for (int i = 0; i < OTW; ++i) acc[i] = make_float2(0.f, 0.f);
@@ -217,8 +234,7 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
           for (int kx = 0; kx < K; ++kx) wk[kx] = __half22float2(__ldg(wd2 + (ky * K + kx) * cm2));
 #pragma unroll
           for (int ixl = 0; ixl < NIX; ++ixl) {
-            const float2 v = __half22float2(
-                *reinterpret_cast<const __half2*>(ebase + (ky * kPatch + ixl) * p.e_pitch));
+            const float2 v = h2_bits_to_f2(lds_b32(ebase + (ky * kPatch + ixl) * kEPitch));
 #pragma unroll
             for (int kx = 0; kx < K; ++kx) {
               if ((ixl - kx) >= 0 && (ixl - kx) % S == 0 && (ixl - kx) / S < OTW)
@@ -230,13 +246,17 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
         __half2* orow = reinterpret_cast<__half2*>(p.out) +
                         ((static_cast<size_t>(tl.n) * p.ho + oy0 + oyl) * p.wo + ox0) * cm2 +
                         (cbase >> 1) + cp;
+#pragma unroll
+        for (int i = 0; i < OTW; ++i) acc[i] = __fadd2_rn(acc[i], bd);
+#pragma unroll
+        for (int i = 0; i + 1 < OTW; i += 2) apply_act4<ACT>(acc[i], acc[i + 1]);
+        if (OTW & 1) acc[OTW - 1] = apply_act2<ACT>(acc[OTW - 1]);
         float2 ssum = make_float2(0.f, 0.f);
 #pragma unroll
         for (int oxl = 0; oxl < OTW; ++oxl) {
           if (oxl < cols) {
-            const float2 o = apply_act2<ACT>(__fadd2_rn(acc[oxl], bd));
-            if (HAS_SE) ssum = __fadd2_rn(ssum, o);
-            orow[static_cast<size_t>(oxl) * cm2] = __floats2half2_rn(o.x, o.y);
+            if (HAS_SE) ssum = __fadd2_rn(ssum, acc[oxl]);
+            orow[static_cast<size_t>(oxl) * cm2] = __floats2half2_rn(acc[oxl].x, acc[oxl].y);
           }
         }
         if (HAS_SE) {
@@ -316,7 +336,6 @@ extern "C" int edet_mbconv_expand_dw(const edet_half* x, const edet_half* we, co
   p.oth = p.otw = (kPatch - k) / stride + 1;
   p.tiles_y = ceil_div(p.ho, p.oth); p.tiles_x = ceil_div(p.wo, p.otw);
   p.total_tiles = n * p.tiles_y * p.tiles_x * p.num_chunks;
-  p.e_pitch = p.ch * 2 + 16;   // (pitch / 16) odd -> conflict-free 128-bit row writes
   int cols = 32;
   while (cols < 2 * p.ch) cols *= 2;
   p.tmem_cols = cols;
@@ -325,7 +344,7 @@ extern "C" int edet_mbconv_expand_dw(const edet_half* x, const edet_half* we, co
     p.block_k = bk;
     p.a_bytes = kPatchPx * bk * 2;
     p.b_bytes = ((p.ch * bk * 2 + 1023) / 1024) * 1024;
-    smem_bytes = 1024 + p.a_bytes + p.b_bytes + kPatchPx * p.e_pitch + p.ch * 8 + 64;
+    smem_bytes = 1024 + p.a_bytes + p.b_bytes + kPatchPx * kEPitch + p.ch * 8 + 64;
     if (smem_bytes <= 113 * 1024 || bk == 32) break;   // two CTAs per SM, else settle for 32
   }
   p.num_k_blocks = ceil_div(cin, p.block_k);

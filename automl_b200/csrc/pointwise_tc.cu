@@ -252,10 +252,12 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                 b1 = make_float4(bb[4], bb[5], bb[6], bb[7]);
               }
               float2 o2[4];
-              o2[0] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 0], v[jj * 8 + 1]), make_float2(b0.x, b0.y)));
-              o2[1] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 2], v[jj * 8 + 3]), make_float2(b0.z, b0.w)));
-              o2[2] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 4], v[jj * 8 + 5]), make_float2(b1.x, b1.y)));
-              o2[3] = apply_act2<ACT>(__fadd2_rn(make_float2(v[jj * 8 + 6], v[jj * 8 + 7]), make_float2(b1.z, b1.w)));
+              o2[0] = __fadd2_rn(make_float2(v[jj * 8 + 0], v[jj * 8 + 1]), make_float2(b0.x, b0.y));
+              o2[1] = __fadd2_rn(make_float2(v[jj * 8 + 2], v[jj * 8 + 3]), make_float2(b0.z, b0.w));
+              o2[2] = __fadd2_rn(make_float2(v[jj * 8 + 4], v[jj * 8 + 5]), make_float2(b1.x, b1.y));
+              o2[3] = __fadd2_rn(make_float2(v[jj * 8 + 6], v[jj * 8 + 7]), make_float2(b1.z, b1.w));
+              apply_act4<ACT>(o2[0], o2[1]);
+              apply_act4<ACT>(o2[2], o2[3]);
               float o[8] = {o2[0].x, o2[0].y, o2[1].x, o2[1].y, o2[2].x, o2[2].y, o2[3].x, o2[3].y};
               if (HAS_RES) {
                 if (row_ok && col < p.nout) {

@@ -87,8 +87,8 @@ stem_kernel(const float* __restrict__ in, __half* __restrict__ out, const __half
         float f0[8], f1[8];
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          const float2 r0 = apply_act2<ACT>(acc0[g * 4 + p]);
-          const float2 r1 = apply_act2<ACT>(acc1[g * 4 + p]);
+          float2 r0 = acc0[g * 4 + p], r1 = acc1[g * 4 + p];
+          apply_act4<ACT>(r0, r1);
           f0[2 * p] = r0.x; f0[2 * p + 1] = r0.y;
           f1[2 * p] = r1.x; f1[2 * p + 1] = r1.y;
         }

@@ -56,7 +56,8 @@ class Engine(object):
   """One network instance bound to one device, one batch size and one image size."""
 
   def __init__(self, config, weights, batch_size, device='cuda:0', pw_impl=ops.PW_TCGEN05,
-               use_cuda_graph=True, image_id_base=0):
+               use_cuda_graph=True, image_id_base=0, fuse_mbconv_front=True,
+               fuse_sepconv=True, fuse_sepconv_nodes=False):
     if not torch.cuda.is_available():
       raise RuntimeError('automl_b200.Engine needs a CUDA device; there is no CPU fallback')
     self.config = config
@@ -66,6 +67,9 @@ class Engine(object):
     self.pw_impl = pw_impl
     self.use_cuda_graph = use_cuda_graph
     self.image_id_base = image_id_base
+    self.fuse_mbconv_front = fuse_mbconv_front
+    self.fuse_sepconv = fuse_sepconv              # head tower layers: dw + pw in one kernel
+    self.fuse_sepconv_nodes = fuse_sepconv_nodes  # BiFPN nodes (measured slower than the pair)
     self.act = utils.activation_code(a.act_type)
     self._graph = None
     self._ops = []          # (name, callable)
@@ -156,13 +160,20 @@ class Engine(object):
       h, wd = cur_hw
       x_in = cur
       mid = x_in
+      # Blocks whose expanded map is large and whose depthwise is 3x3 stride 2 run the fused
+      # front half (expand in TMEM, depthwise from shared memory): measured faster than the two
+      # separate kernels on B200 (profiles/); the other blocks keep the two-kernel form.
+      fuse_front = (self.fuse_mbconv_front and b.expand_name and b.kernel_size == 3 and
+                    b.stride == 2 and b.input_filters <= 64 and h * wd >= 1600)
+      exp_wt = exp_b = None
       if b.expand_name:
         s, sh = _bn_fold(w, '%s/%s' % (scope, b.expand_bn), eps)
         kw = np.asarray(w['%s/%s/kernel' % (scope, b.expand_name)], np.float64)[0, 0]  # [Cin,Cmid]
-        wt = self._dev((kw * s).T, f16)
-        bias = self._dev(sh, f32)
-        mid = self._buf(b.name + '/expand', (n, h, wd, b.mid_filters))
-        self._pw(b.name + '/expand', x_in, wt, bias, mid, act)
+        exp_wt = self._dev((kw * s).T, f16)
+        exp_b = self._dev(sh, f32)
+        if not fuse_front:
+          mid = self._buf(b.name + '/expand', (n, h, wd, b.mid_filters))
+          self._pw(b.name + '/expand', x_in, exp_wt, exp_b, mid, act)
       # depthwise
       s, sh = _bn_fold(w, '%s/%s' % (scope, b.dw_bn), eps)
       kd = np.asarray(w[scope + '/depthwise_conv2d/depthwise_kernel'], np.float64)[..., 0]  # [k,k,C]
@@ -177,13 +188,25 @@ class Engine(object):
         partial = se_acc[se_index % 2].view(-1)[:n * b.mid_filters].view(n, b.mid_filters)
         next_zero = se_acc[(se_index + 1) % 2]
         se_index += 1
-      self._add(b.name + '/dw',
-                lambda mid=mid, dwo=dwo, dw_w=dw_w, dw_b=dw_b, partial=partial, b=b:
-                ops.depthwise_conv(mid, dwo, dw_w, dw_b, act, b.kernel_size, b.stride, partial),
-                kind='depthwise_k%ds%d' % (b.kernel_size, b.stride),
-                nbytes=2 * n * b.mid_filters * (h * wd + ho * wo) + 2 * b.kernel_size**2 * b.mid_filters
-                + (8 * partial.numel() if partial is not None else 0),
-                flops=2 * b.kernel_size**2 * n * b.mid_filters * ho * wo)
+      if fuse_front:
+        self._add(b.name + '/expand_dw',
+                  lambda x_in=x_in, exp_wt=exp_wt, exp_b=exp_b, dwo=dwo, dw_w=dw_w, dw_b=dw_b,
+                  partial=partial, b=b:
+                  ops.mbconv_expand_dw(x_in, exp_wt, exp_b, dw_w, dw_b, dwo, act, b.kernel_size,
+                                       b.stride, partial),
+                  kind='mbconv_expand_dw',
+                  nbytes=2 * n * (h * wd * b.input_filters + ho * wo * b.mid_filters)
+                  + 2 * b.mid_filters * (b.input_filters + b.kernel_size**2)
+                  + (8 * partial.numel() if partial is not None else 0),
+                  flops=2 * n * b.mid_filters * (h * wd * b.input_filters + b.kernel_size**2 * ho * wo))
+      else:
+        self._add(b.name + '/dw',
+                  lambda mid=mid, dwo=dwo, dw_w=dw_w, dw_b=dw_b, partial=partial, b=b:
+                  ops.depthwise_conv(mid, dwo, dw_w, dw_b, act, b.kernel_size, b.stride, partial),
+                  kind='depthwise_k%ds%d' % (b.kernel_size, b.stride),
+                  nbytes=2 * n * b.mid_filters * (h * wd + ho * wo) + 2 * b.kernel_size**2 * b.mid_filters
+                  + (8 * partial.numel() if partial is not None else 0),
+                  flops=2 * b.kernel_size**2 * n * b.mid_filters * ho * wo)
       # project (+SE folded into per-image weights, + skip)
       s, sh = _bn_fold(w, '%s/%s' % (scope, b.project_bn), eps)
       kp = np.asarray(w['%s/%s/kernel' % (scope, b.project_name)], np.float64)[0, 0]  # [Cmid,Cout]
@@ -197,13 +220,14 @@ class Engine(object):
         w2 = self._dev(np.asarray(w[scope + '/se/conv2d_1/kernel'], np.float64)[0, 0], f32)  # [se,C]
         b2 = self._dev(w[scope + '/se/conv2d_1/bias'], f32)
         gate = self._buf(b.name + '/se_gate', (n, b.mid_filters), f32)
+        hidden = self._buf(b.name + '/se_hidden', (n, b.se_filters), f32)
         wt_scaled = self._buf(b.name + '/proj_w', (n, b.output_filters, b.mid_filters))
         inv_hw = 1.0 / float(ho * wo)
         self._add(b.name + '/se',
                   lambda partial=partial, inv_hw=inv_hw, w1=w1, b1=b1, w2=w2, b2=b2, gate=gate,
-                  proj_wt=proj_wt, wt_scaled=wt_scaled, next_zero=next_zero:
+                  proj_wt=proj_wt, wt_scaled=wt_scaled, next_zero=next_zero, hidden=hidden:
                   ops.se_fc(partial, inv_hw, w1, b1, w2, b2, gate, act, proj_wt, wt_scaled,
-                            next_zero),
+                            next_zero, hidden),
                   kind='se_fc', nbytes=8 * partial.numel() + 2 * proj_wt.numel() + 2 * wt_scaled.numel(),
                   kernels=2)
         self._pw(b.name + '/project', dwo, wt_scaled, proj_b, y, utils.ACT_NONE, residual=res,
@@ -270,6 +294,10 @@ class Engine(object):
       pyramid.append(out)
 
     mode_code = {'same': ops.RS_SAME, 'up': ops.RS_UP, 'down': ops.RS_DOWN}
+    # the fused separable-conv kernel covers D0-D2 widths and the swish / relu6 networks; wider
+    # feature networks keep the fuse_dw + pointwise pair
+    fuse_sep = ((self.fuse_sepconv or self.fuse_sepconv_nodes) and F <= ops.SEPCONV_MAX_C and
+                act in (utils.ACT_SWISH, utils.ACT_RELU6))
     for ci, cell in enumerate(a.cells):
       cell_feats = list(pyramid)
       for node in cell['nodes']:
@@ -307,14 +335,21 @@ class Engine(object):
         pw_wt = self._dev((kp * s).T, f16)
         pw_b = self._dev(cb * s + sh, f32)
         hh, ww = node.hw
-        tmp = self._buf(node.scope + '/fused_dw', (n, hh, ww, F))
         out = self._buf(node.scope + '/out', (n, hh, ww, F))
-        self._add(node.scope + '/fuse_dw',
-                  lambda specs=specs, dw_w=dw_w, tmp=tmp: ops.fuse_dw(specs, dw_w, tmp, act),
-                  kind='bifpn_fuse_dw',
-                  nbytes=2 * (sum(sp[0].numel() for sp in specs) + tmp.numel()) + 18 * F,
-                  flops=2 * 9 * tmp.numel(), needs=needs)
-        self._pw(node.scope + '/pw', tmp, pw_wt, pw_b, out, utils.ACT_NONE)
+        in_bytes = 2 * sum(sp[0].numel() for sp in specs)
+        if fuse_sep and self.fuse_sepconv_nodes:
+          self._add(node.scope + '/sepconv',
+                    lambda specs=specs, dw_w=dw_w, pw_wt=pw_wt, pw_b=pw_b, out=out:
+                    ops.sepconv(specs, act, dw_w, pw_wt, pw_b, out, utils.ACT_NONE),
+                    kind='sepconv_tc', nbytes=in_bytes + 2 * out.numel() + 18 * F + 2 * F * F,
+                    flops=2 * (9 + F) * out.numel(), needs=needs)
+        else:
+          tmp = self._buf(node.scope + '/fused_dw', (n, hh, ww, F))
+          self._add(node.scope + '/fuse_dw',
+                    lambda specs=specs, dw_w=dw_w, tmp=tmp: ops.fuse_dw(specs, dw_w, tmp, act),
+                    kind='bifpn_fuse_dw', nbytes=in_bytes + 2 * tmp.numel() + 18 * F,
+                    flops=2 * 9 * tmp.numel(), needs=needs)
+          self._pw(node.scope + '/pw', tmp, pw_wt, pw_b, out, utils.ACT_NONE)
         cell_feats.append(out)
       pyramid = [cell_feats[cell['out_index'][l]] for l in a.levels]
     self.fpn_feats = dict(zip(a.levels, pyramid))
@@ -348,10 +383,17 @@ class Engine(object):
           wt = self._dev((pws[i] * s).T, f16)
           bias = self._dev(pbs[i] * s + sh, f32)
           y = ping if i % 2 == 0 else pong
-          self._add('%s/l%d/dw%d' % (scope, level, i),
-                    lambda x=x, t=t, dwk=dws[i]: ops.depthwise_conv(x, t, dwk, None, utils.ACT_NONE, 3, 1),
-                    kind='depthwise_k3s1', nbytes=4 * t.numel() + 18 * F, flops=18 * t.numel())
-          self._pw('%s/l%d/pw%d' % (scope, level, i), t, wt, bias, y, act)
+          if fuse_sep and self.fuse_sepconv:
+            self._add('%s/l%d/sep%d' % (scope, level, i),
+                      lambda x=x, dwk=dws[i], wt=wt, bias=bias, y=y:
+                      ops.sepconv([(x, ops.RS_SAME, None, 1.0)], utils.ACT_NONE, dwk, wt, bias, y, act),
+                      kind='sepconv_tc', nbytes=4 * y.numel() + 18 * F + 2 * F * F,
+                      flops=2 * (9 + F) * y.numel())
+          else:
+            self._add('%s/l%d/dw%d' % (scope, level, i),
+                      lambda x=x, t=t, dwk=dws[i]: ops.depthwise_conv(x, t, dwk, None, utils.ACT_NONE, 3, 1),
+                      kind='depthwise_k3s1', nbytes=4 * t.numel() + 18 * F, flops=18 * t.numel())
+            self._pw('%s/l%d/pw%d' % (scope, level, i), t, wt, bias, y, act)
           x = y
         out = self._buf('%s/l%d/out' % (scope, level), (n, hh, ww, ld))
         out.zero_()

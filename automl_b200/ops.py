@@ -86,15 +86,20 @@ def mbconv_expand_dw(x, we, bias_e, wd, bias_d, out, act, k, stride, se_sum=None
             act, _stream())
 
 
-def se_fc(se_sum, inv_hw, w1, b1, w2, b2, gate, act, wt=None, wt_scaled=None, zero_buf=None):
-  """se_sum int64 [N, C]; zero_buf: int64 [N, Cz] buffer cleared by the same launch."""
+def se_fc(se_sum, inv_hw, w1, b1, w2, b2, gate, act, wt=None, wt_scaled=None, zero_buf=None,
+          hidden=None):
+  """se_sum int64 [N, C]; zero_buf: int64 [N, Cz] buffer cleared by the same launch; hidden:
+  float32 [N, se] scratch for the squeezed activations (allocated here when not given)."""
   n, c = gate.shape
   se = w1.shape[0]
+  if hidden is None:
+    hidden = torch.empty(n, se, dtype=torch.float32, device=gate.device)
   nout = wt.shape[0] if wt is not None else 0
   zc = zero_buf.shape[1] if zero_buf is not None else 0
   _lib.call('edet_se_fc', _ptr(se_sum, torch.int64), ctypes.c_float(inv_hw),
             _ptr(w1, torch.float32), _ptr(b1, torch.float32), _ptr(w2, torch.float32),
-            _ptr(b2, torch.float32), _ptr(gate, torch.float32), _ptr(wt, torch.float16),
+            _ptr(b2, torch.float32), _ptr(hidden, torch.float32), _ptr(gate, torch.float32),
+            _ptr(wt, torch.float16),
             _ptr(wt_scaled, torch.float16), _ptr(zero_buf, torch.int64), zc, n, c, se, nout, act,
             _stream())
 
@@ -119,6 +124,23 @@ def fuse_dw(specs, dw_w, out, act):
   arr = make_fuse_inputs(specs)
   _lib.call('edet_fuse_dw', arr, len(specs), _ptr(dw_w, torch.float16),
             _ptr(out, torch.float16), n, h, wd, c, act, _stream())
+
+
+SEPCONV_MAX_C = 128   # edet_sepconv limits (c and nout)
+
+
+def sepconv(specs, pre_act, dw_w, pw_wt, bias, out, post_act, nout=None):
+  """Fused fuse_dw + pointwise_conv: specs as in fuse_dw, pw_wt fp16 [nout, c], out fp16
+  [N,h,w,ldo] (ldo >= nout)."""
+  n, h, wd, ldo = out.shape
+  c = pw_wt.shape[-1]
+  n_out = nout if nout is not None else pw_wt.shape[0]
+  for t, _, _, _ in specs:
+    _ptr(t, torch.float16)
+  arr = make_fuse_inputs(specs)
+  _lib.call('edet_sepconv', arr, len(specs), pre_act, _ptr(dw_w, torch.float16),
+            _ptr(pw_wt, torch.float16), _ptr(bias, torch.float32), _ptr(out, torch.float16), ldo,
+            n, h, wd, c, n_out, post_act, _stream())
 
 
 def max_pool(x, out, pool, stride):

@@ -137,6 +137,7 @@ int edet_depthwise_conv(const edet_half* in, edet_half* out, const edet_half* w,
  * Replaces backbone/efficientnet_model.py:183-195 (SE.call) and the multiply at :195.
  *   se_sum   int64 [n, c]               w1 float32 [se][c], b1 [se], w2 float32 [se][c] (the
  *            second FC stored TRANSPOSED so both FCs read coalesced), b2 [c]
+ *   hidden   float32 [n, se] (output / scratch: the squeezed activations)
  *   gate     float32 [n, c] (output, always written)
  *   wt       half [nout][c] project weights (nullable -> only the gate is produced)
  *   wt_scaled half [n][nout][c]
@@ -144,7 +145,7 @@ int edet_depthwise_conv(const edet_half* in, edet_half* out, const edet_half* w,
  *            block, so no separate memset launch is needed)
  */
 int edet_se_fc(const int64_t* se_sum, float inv_hw, const float* w1, const float* b1,
-               const float* w2, const float* b2, float* gate, const edet_half* wt,
+               const float* w2, const float* b2, float* hidden, float* gate, const edet_half* wt,
                edet_half* wt_scaled, int64_t* zero_buf, int zero_count, int n, int c, int se,
                int nout, int act, edet_stream_t stream);
 
@@ -165,6 +166,20 @@ typedef struct {
 } edet_fuse_input;
 int edet_fuse_dw(const edet_fuse_input* h_inputs, int n_inputs, const edet_half* dw_w,
                  edet_half* out, int n, int h, int wd, int c, int act, edet_stream_t stream);
+
+/* Fused separable convolution of the feature network / head towers (tcgen05):
+ *   out = post_act( pointwise( depthwise3x3( pre_act( sum_i weight_i * resample_i(input_i) ) ) ) + bias )
+ * i.e. edet_fuse_dw followed by edet_pointwise_conv without the [n,h,w,c] intermediate in HBM
+ * (the depthwise result is rounded to fp16 in shared memory, exactly as the pair rounds it in
+ * global memory).  Replaces a whole BiFPN node (efficientdet_arch.py:478-544: pre_act = the
+ * network activation, post_act = NONE) or a head tower layer (:149-191 / :206-249: one input,
+ * weight 1, pre_act = NONE, post_act = the activation after the per-level BN folded into
+ * pw_wt / bias).
+ *   dw_w half [9][c], pw_wt half [nout][c], bias float32 [nout], out half [n,h,wd,ldo]
+ *   c % 8 == 0, c <= 128; nout % 8 == 0, nout <= 128; ldo >= nout, ldo % 8 == 0. */
+int edet_sepconv(const edet_fuse_input* h_inputs, int n_inputs, int pre_act, const edet_half* dw_w,
+                 const edet_half* pw_wt, const float* bias, edet_half* out, int ldo, int n, int h,
+                 int wd, int c, int nout, int post_act, edet_stream_t stream);
 
 /* Max-pool 'SAME' (padded cells never win). Replaces efficientdet_arch.py:103-112 for the
  * P6/P7/P8 extra levels (efficientdet_arch.py:369-387). */

@@ -33,7 +33,10 @@ def timeit(fn, iters=20):
   return a.elapsed_time(b) / iters
 
 
+ONLY = sys.argv[2].split(',') if len(sys.argv) > 2 else None
 for name, h, cin, cmid, k, s in SHAPES:
+  if ONLY and name not in ONLY:
+    continue
   g = torch.Generator().manual_seed(1)
   x = torch.randn(N, h, h, cin, generator=g).half().to(DEV)
   we = (torch.randn(cmid, cin, generator=g) / cin**0.5).half().to(DEV)

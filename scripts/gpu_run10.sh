@@ -1,0 +1,7 @@
+set -x
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -1
+timeout 1200 python -m pytest tests -q -m gpu --timeout 300 -x 2>&1 | tail -5
+
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --profile-out gpurun_out/ops_r1j.json > gpurun_out/bench10.log 2>&1; tail -1 gpurun_out/bench10.log | cut -c1-400

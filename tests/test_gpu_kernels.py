@@ -173,14 +173,15 @@ def test_mbconv_expand_dw(case):
     assert torch.equal(again, se)
 
 
-def test_se_fc():
+@pytest.mark.parametrize('shape', [(3, 96, 4, 24), (2, 144, 6, 24), (2, 1152, 48, 320)])
+def test_se_fc(shape):
   ops = _ops()
-  n, c, se, nout = 3, 96, 4, 24
+  n, c, se, nout = shape
   g = torch.Generator().manual_seed(5)
   sums = torch.randn(n, c, generator=g) * 20
   se_sum = torch.round(sums.double() * 2.0**20).to(torch.int64)
-  nxt = torch.full((n, 144), 123, dtype=torch.int64, device=DEV)
-  w1, b1 = torch.randn(se, c, generator=g) * 0.2, torch.randn(se, generator=g) * 0.1
+  nxt = torch.full((n, 1160), 123, dtype=torch.int64, device=DEV)
+  w1, b1 = torch.randn(se, c, generator=g) * 2.0 / c**0.5, torch.randn(se, generator=g) * 0.1
   w2, b2 = torch.randn(c, se, generator=g) * 0.5, torch.randn(c, generator=g) * 0.1
   wt = torch.randn(nout, c, generator=g).half()
   gate = torch.empty(n, c, device=DEV)
@@ -241,6 +242,67 @@ def test_fuse_dw_all_modes():
     fused = fused * torch.sigmoid(fused)
     ref = eo.depthwise_conv2d_same(fused, dwk.double().unsqueeze(-1)).permute(0, 2, 3, 1)
     assert torch.allclose(out.cpu().double(), ref, rtol=2e-3, atol=2e-3), (h, w)
+
+
+SEP_CASES = [
+    # n, (h, w), c, nout, pre, post, inputs [(mode, (h, w))]
+    (2, (20, 20), 64, 64, utils.ACT_SWISH, utils.ACT_NONE, ['same', 'up']),        # td node
+    (2, (10, 10), 64, 64, utils.ACT_SWISH, utils.ACT_NONE, ['same', 'same', 'down']),  # bu node
+    (1, (13, 21), 88, 88, utils.ACT_SWISH, utils.ACT_NONE, ['same', 'up']),        # D1 width, 2 atoms
+    (2, (5, 5), 64, 64, utils.ACT_NONE, utils.ACT_SWISH, ['same']),                # tower layer, tiny level
+    (1, (40, 40), 64, 64, utils.ACT_NONE, utils.ACT_SWISH, ['same']),              # several tiles per CTA
+    (1, (9, 17), 112, 112, utils.ACT_RELU6, utils.ACT_NONE, ['same', 'down']),
+    (3, (80, 80), 64, 64, utils.ACT_NONE, utils.ACT_SWISH, ['same']),              # persistent loop
+]
+
+
+@pytest.mark.parametrize('case', SEP_CASES)
+def test_sepconv(case):
+  """edet_sepconv == edet_fuse_dw + edet_pointwise_conv bit for bit (same fp16 rounding of the
+  depthwise result), and both match the float64 restatement."""
+  ops = _ops()
+  n, (h, w), c, nout, pre, post, modes = case
+  g = torch.Generator().manual_seed(31 + h + c)
+  specs, ref_in = [], []
+  wsum = float(len(modes))
+  for i, m in enumerate(modes):
+    if m == 'same':
+      hh, ww, pool = h, w, None
+    elif m == 'up':
+      hh, ww, pool = -(-h // 2), -(-w // 2), None
+    else:
+      hh, ww, pool = h * 2 - (h % 2), w * 2 - (w % 2), (3, 3, 2, 2)
+    t = torch.randn(n, hh, ww, c, generator=g).half()
+    wgt = (i + 1.0) / (wsum * (wsum + 1) / 2)
+    specs.append((t.to(DEV), {'same': ops.RS_SAME, 'up': ops.RS_UP, 'down': ops.RS_DOWN}[m], pool, wgt))
+    ref_in.append((t, m, wgt))
+  dw_w = (torch.randn(9, c, generator=g) / 3).half()
+  pw = (torch.randn(nout, c, generator=g) / c**0.5).half()
+  bias = torch.randn(nout, generator=g) * 0.1
+  ldo = nout + 8
+  out = torch.full((n, h, w, ldo), 7.0, dtype=torch.float16, device=DEV)
+  ops.sepconv(specs, pre, dw_w.to(DEV), pw.to(DEV), bias.to(DEV), out, post, nout=nout)
+  tmp = torch.empty(n, h, w, c, dtype=torch.float16, device=DEV)
+  two = torch.full((n, h, w, ldo), 7.0, dtype=torch.float16, device=DEV)
+  ops.fuse_dw(specs, dw_w.to(DEV), tmp, pre)
+  ops.pointwise_conv(tmp, pw.to(DEV), bias.to(DEV), two, post, rows=n * h * w, nout=nout)
+  torch.cuda.synchronize()
+  assert torch.equal(out[..., :nout], two[..., :nout])
+  assert bool((out[..., nout:] == 7.0).all())       # the padding columns are not touched
+  # float64 restatement
+  fused = 0
+  for t, m, wgt in ref_in:
+    x = t.double().permute(0, 3, 1, 2)
+    if m == 'up':
+      x = eo.resize_nearest_tf1(x, h, w)
+    elif m == 'down':
+      x = eo.max_pool_same(x, (3, 3), (2, 2))
+    fused = fused + x * float(np.float32(wgt))
+  fused = act_ref(fused, pre)
+  d = eo.depthwise_conv2d_same(fused, dw_w.double().view(3, 3, c, 1), 1).permute(0, 2, 3, 1)
+  ref = act_ref(d.half().double() @ pw.double().t() + bias.double(), post)
+  got = out[..., :nout].cpu().double()
+  assert torch.allclose(got, ref, rtol=3e-3, atol=3e-3), float((got - ref).abs().max())
 
 
 def test_max_pool():
