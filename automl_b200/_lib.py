@@ -14,6 +14,7 @@ c_void_p, c_int, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_fl
 
 RS_SAME, RS_UP, RS_DOWN = 0, 1, 2
 PW_TCGEN05, PW_SIMT = 0, 1
+NMS_HARD, NMS_DIOU, NMS_GAUSSIAN, NMS_LINEAR = 0, 1, 2, 3
 
 
 class FuseInput(ctypes.Structure):
@@ -57,6 +58,9 @@ SIGNATURES = {
     'edet_nms_v5': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                             c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_void_p]),
+    'edet_per_class_nms': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                   c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]),
 }
 
 _lib = None

@@ -594,6 +594,14 @@ class Engine(object):
       self.wait_detections()
     return self.detections
 
+  def pre_nms_only(self):
+    """Runs pre-NMS (class arg-max, sigmoid, box decode) on the current head outputs and returns
+    the buffer set {'boxes' [N,K,4], 'scores' [N,K], 'classes' [N,K]} (for the per-class NMS
+    path, automl_b200/postprocess.py)."""
+    with torch.cuda.device(self.device):
+      self._pre_ops[self._cur]()
+    return self._post[self._cur]
+
   def nms_fallback_count(self):
     """Images of the last run that needed the full-queue NMS kernel (fast path not provable)."""
     flags = self._post[self._cur]['work'][-4 * self.n:].view(torch.int32)

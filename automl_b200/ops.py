@@ -176,3 +176,24 @@ def nms_v5(boxes, scores, classes, image_scales, image_id_base, max_output_size,
             ctypes.c_float(soft_nms_sigma), ctypes.c_float(clip_hw[0]),
             ctypes.c_float(clip_hw[1]), _ptr(detections, torch.float32),
             _ptr(sel_index, torch.int32), _ptr(valid, torch.int32), _ptr(work), _stream())
+
+
+NMS_METHODS = {'hard': _lib.NMS_HARD, '': _lib.NMS_HARD, None: _lib.NMS_HARD, 'diou': _lib.NMS_DIOU,
+               'gaussian': _lib.NMS_GAUSSIAN, 'linear': _lib.NMS_LINEAR}
+
+
+def per_class_nms(boxes, scores, classes, image_ids, image_scales, num_classes, max_boxes_to_draw,
+                  method, iou_thresh, detections, keep_index, num_valid):
+  """nms_np.per_class_nms on the device (hard / diou): boxes fp32 [N,K,4] (ymin,xmin,ymax,xmax),
+  scores fp32 [N,K], classes i32 [N,K], image_ids / image_scales fp32 [N] or None ->
+  detections fp32 [N,max_boxes,7], keep_index i32 [N,max_boxes], num_valid i32 [N]."""
+  n, k = scores.shape
+  if method not in NMS_METHODS:
+    raise ValueError('Unknown NMS method: {}'.format(method))
+  # nms_np: `iou_thresh or 0.5` (hard / diou), compared in float32
+  thr = float(iou_thresh) if iou_thresh else 0.5
+  _lib.call('edet_per_class_nms', _ptr(boxes, torch.float32), _ptr(scores, torch.float32),
+            _ptr(classes, torch.int32), _ptr(image_ids, torch.float32),
+            _ptr(image_scales, torch.float32), n, k, num_classes, max_boxes_to_draw,
+            NMS_METHODS[method], ctypes.c_float(thr), _ptr(detections, torch.float32),
+            _ptr(keep_index, torch.int32), _ptr(num_valid, torch.int32), _stream())

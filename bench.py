@@ -110,7 +110,7 @@ def cpu_baseline(config, weights, images, seconds_budget=25.0):
   po.det_post_process(params, {l: v.numpy() for l, v in cls_o.items()},
                       {l: v.numpy() for l, v in box_o.items()}, np.ones(1, np.float32))
   one = time.perf_counter() - t0
-  nimg = int(max(1, min(8, seconds_budget // max(one, 1e-3))))
+  nimg = int(max(1, min(BATCH, len(images), seconds_budget // max(one, 1e-3))))
   sample = images[:nimg]
   t0 = time.perf_counter()
   cls_o, box_o = orc(sample)
@@ -269,13 +269,23 @@ def main():
                 'per_kind': {n: {'ms': round(k['ms'], 4), 'GBps': round(k['bytes'] / max(k['ms'], 1e-9) / 1e6, 1),
                                  'TFLOPs': round(k['flops'] / max(k['ms'], 1e-9) / 1e9, 2),
                                  'launches': k['launches']} for n, k in sorted(kinds.items())}}
+    # DRAM bytes of the dominant kernel family per forward, from the committed ncu capture of
+    # this same command (profiles/r1_traffic.json, made by scripts/gpu_final.sh)
+    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if os.path.exists(tpath):
+      with open(tpath) as f:
+        fam_key = 'depthwise_kernel' if fam is dw else 'pointwise_tc_kernel'
+        t = json.load(f)['per_forward'].get(fam_key)
+      if t:
+        roofline['traffic'] = int((t['dram_read_MB'] + t['dram_write_MB']) * 1e6)
+        roofline['traffic_source'] = 'profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, family sum per forward)'
     if args.profile_out:
       with open(args.profile_out, 'w') as f:
         json.dump({'ops': rows, 'kinds': roofline['per_kind'], 'sum_ms': total_ms}, f, indent=1)
     base = None
     if not args.no_cpu_baseline:
       w = weights_lib.synthetic_weights(arch.DetArch(config), 0)
-      base = cpu_baseline(config, w, eng.input[:8].cpu().numpy())
+      base = cpu_baseline(config, w, eng.input.cpu().numpy())
     line = {
         'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(3, args.warmup),

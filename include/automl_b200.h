@@ -218,6 +218,32 @@ int edet_nms_v5(const float* boxes, const float* scores, const int32_t* classes,
                 float clip_h, float clip_w, float* detections, int32_t* sel_index,
                 int32_t* valid, void* work, edet_stream_t stream);
 
+/*
+ * CUDA replacement for nms_np.per_class_nms (nms_np.py:220-264) with the `hard` (nms_np.py:89-126)
+ * and `diou` (:28-86) methods: per class greedy NMS in descending score order, float32 "+1 pixel"
+ * IoU in nms_np's order of operations (keep decisions bit-identical to NumPy's), survivors of all
+ * classes merged, top max_boxes_to_draw by score.  Replaces the tf.numpy_function call of
+ * tf2/postprocess.py:541-556 (generate_detections with nms_configs.pyfunc).
+ *   boxes float32 [n, k, 4] (ymin, xmin, ymax, xmax), scores float32 [n, k], classes int32 [n, k]
+ *   (0-based; values outside [0, num_classes) are ignored), image_ids / image_scales float32 [n]
+ *   or NULL (row index / 1.0)
+ *   detections float32 [n, max_boxes_to_draw, 7]: [image_id, xmin, ymin, xmax, ymax, score,
+ *   class + 1], boxes x image_scale; rows beyond the survivors are [image_id, 0,0,0,0, -1e5, 0]
+ *   keep_index int32 [n, max_boxes_to_draw]: anchor index of each row (-1 for dummy rows)
+ *   num_valid int32 [n]
+ * Equal scores: the higher anchor index first (NumPy's unstable argsort leaves this undefined).
+ * EDET_NMS_GAUSSIAN / EDET_NMS_LINEAR return EDET_ERR_UNSUPPORTED (not built yet).
+ */
+#define EDET_NMS_HARD 0
+#define EDET_NMS_DIOU 1
+#define EDET_NMS_GAUSSIAN 2
+#define EDET_NMS_LINEAR 3
+int edet_per_class_nms(const float* boxes, const float* scores, const int32_t* classes,
+                       const float* image_ids, const float* image_scales, int n, int k,
+                       int num_classes, int max_boxes_to_draw, int method, float iou_thresh,
+                       float* detections, int32_t* keep_index, int32_t* num_valid,
+                       edet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,51 @@ def pw(m, k, n, act, res=False, per_image=False):
     ops.pointwise_conv(a, w, b, out, act, residual=r, rows=m // N, batch=N, nout=n)
 
 
+def stem():
+  x = torch.randn(N, 640, 640, 3, device=dev)
+  w = torch.randn(27, 32, device=dev).half()
+  b = torch.randn(32, device=dev)
+  out = torch.empty(N, 320, 320, 32, dtype=torch.float16, device=dev)
+  for _ in range(reps):
+    ops.stem_conv(x, out, w, b, utils.ACT_SWISH)
+
+
+def front(h, cin, cmid, k, s):
+  x = torch.randn(N, h, h, cin, device=dev).half()
+  we = (torch.randn(cmid, cin, device=dev) / cin**0.5).half()
+  be = torch.randn(cmid, device=dev) * 0.1
+  wd = (torch.randn(k * k, cmid, device=dev) / k).half()
+  bd = torch.randn(cmid, device=dev) * 0.1
+  ho = -(-h // s)
+  out = torch.empty(N, ho, ho, cmid, dtype=torch.float16, device=dev)
+  se = torch.zeros(N, cmid, dtype=torch.int64, device=dev)
+  for _ in range(reps):
+    ops.mbconv_expand_dw(x, we, be, wd, bd, out, utils.ACT_SWISH, k, s, se)
+
+
+def tower(h, f=64):
+  x = torch.randn(N, h, h, f, device=dev).half()
+  dwk = (torch.randn(9, f, device=dev) / 3).half()
+  pwk = (torch.randn(f, f, device=dev) / f**0.5).half()
+  b = torch.randn(f, device=dev) * 0.1
+  out = torch.empty(N, h, h, f, dtype=torch.float16, device=dev)
+  for _ in range(reps):
+    ops.sepconv([(x, ops.RS_SAME, None, 1.0)], utils.ACT_NONE, dwk, pwk, b, out, utils.ACT_SWISH)
+
+
+def node(h, f=64):
+  a = torch.randn(N, h, h, f, device=dev).half()
+  u = torch.randn(N, h // 2, h // 2, f, device=dev).half()
+  dwk = (torch.randn(9, f, device=dev) / 3).half()
+  out = torch.empty(N, h, h, f, dtype=torch.float16, device=dev)
+  for _ in range(reps):
+    ops.fuse_dw([(a, ops.RS_SAME, None, 0.6), (u, ops.RS_UP, None, 0.4)], dwk, out, utils.ACT_SWISH)
+
+
+stem()
+front(320, 16, 96, 3, 2)   # blocks_1 fused expand + dw
+tower(80)                  # head tower layer, level 3
+node(80)                   # BiFPN td node, level 3
 dw(320, 32, 3, 1)          # blocks_0 dw
 dw(320, 96, 3, 2)          # blocks_1 dw (largest byte mover)
 dw(80, 240, 5, 1)          # blocks_4 dw

@@ -49,6 +49,16 @@ def make_dets(rng, k, image=512.0, clusters=None):
   return np.column_stack([x1y1, x2y2, scores]).astype(np.float32)
 
 
+def make_dense_dets(rng, k, clusters, size=60.0, jitter=4.0, image=512.0):
+  """Near-duplicate boxes around a few centres (heavy suppression), distinct float32 scores."""
+  centres = rng.uniform(size, image - size, size=(clusters, 2))
+  c = centres[rng.integers(0, clusters, size=k)] + rng.normal(0, jitter, size=(k, 2))
+  wh = size + rng.normal(0, jitter, size=(k, 2))
+  scores = np.unique(rng.uniform(0.01, 0.99, size=4 * k).astype(np.float32))
+  scores = rng.permutation(scores)[:k]
+  return np.column_stack([c - wh / 2, c + wh / 2, scores]).astype(np.float32)
+
+
 def main():
   nms_np, hparams_config, fpn_configs = import_reference()
   rng = np.random.default_rng(20260922)
@@ -86,6 +96,32 @@ def main():
       pc['out_%d_%d' % (ci, mi)] = out
     pc['boxes_%d' % ci], pc['scores_%d' % ci], pc['classes_%d' % ci] = boxes, scores, classes
   np.savez_compressed(os.path.join(OUT, 'nms_np_per_class.npz'), **pc)
+
+  # per_class_nms goldens for the CUDA replacement (hard / diou; tests/test_gpu_kernels.py):
+  # many classes, few classes (long per-class lists), tight clusters (fewer than 100 survivors in
+  # the top 2048 candidates -> several selection rounds on the device), fewer survivors than rows
+  rng2 = np.random.default_rng(7051)
+  hd = {}
+  hd_cases = [(50, 90, None), (600, 90, 15), (5000, 90, 125), (20000, 90, 400), (6000, 3, 40),
+              (12000, 2, 12), (3000, 1, 8)]
+  hd_methods = [dict(method='hard', iou_thresh=None), dict(method='hard', iou_thresh=0.3),
+                dict(method='diou', iou_thresh=None), dict(method='diou', iou_thresh=0.65)]
+  hd_cases += [(8000, 1, -30), (20000, 2, -25), (49104, 90, -300)]   # negative: dense generator
+  for ci, (k, ncls, clusters) in enumerate(hd_cases):
+    d = make_dets(rng2, k, clusters=clusters) if clusters is None or clusters > 0 else \
+        make_dense_dets(rng2, k, -clusters)
+    boxes = d[:, [1, 0, 3, 2]].copy()
+    scores = d[:, 4].copy()
+    classes = rng2.integers(0, ncls, size=k).astype(np.int32)
+    scale = np.asarray([0.75 + 0.25 * ci], np.float32)
+    for mi, cfg in enumerate(hd_methods):
+      cfg = dict(cfg, score_thresh=0.0, sigma=None, max_output_size=100, pyfunc=True, max_nms_inputs=0)
+      hd['out_%d_%d' % (ci, mi)] = nms_np.per_class_nms(
+          boxes, scores, classes, np.asarray([ci + 10], np.float32), scale, ncls, 100, cfg)
+    hd['boxes_%d' % ci], hd['scores_%d' % ci], hd['classes_%d' % ci] = boxes, scores, classes
+    hd['scale_%d' % ci], hd['ncls_%d' % ci] = scale, np.asarray(ncls)
+  hd['methods'] = np.asarray([json.dumps(m) for m in hd_methods])
+  np.savez_compressed(os.path.join(OUT, 'nms_np_per_class_hard.npz'), **hd)
 
   # ---- registry / fpn goldens ---------------------------------------------------------
   reg = {}

@@ -457,3 +457,52 @@ def test_nms_v5_fewer_than_max_and_empty():
   np.testing.assert_array_equal(sel[0].cpu().numpy(), idx)
   np.testing.assert_array_equal(det[0, :, 5].cpu().numpy(), sc)
   assert float(det[1, :, 5].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# nms_np.per_class_nms replacement: rows bit-identical to the REAL reference module's output
+# (tests/golden/nms_np_per_class_hard.npz, written by tests/golden/make_golden.py from
+# /root/reference/efficientdet/nms_np.py)
+@pytest.mark.parametrize('ci', range(10))
+def test_per_class_nms_matches_reference_module(ci):
+  import json
+  import os
+  ops = _ops()
+  g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'nms_np_per_class_hard.npz'))
+  methods = [json.loads(m) for m in g['methods']]
+  boxes, scores, classes = g['boxes_%d' % ci], g['scores_%d' % ci], g['classes_%d' % ci]
+  k = scores.shape[0]
+  n = 2   # image 1 = the same candidates in reversed anchor order (same rows, mirrored indices)
+  b = torch.from_numpy(np.stack([boxes, boxes[::-1]])).to(DEV).contiguous()
+  s_ = torch.from_numpy(np.stack([scores, scores[::-1]])).to(DEV).contiguous()
+  c = torch.from_numpy(np.stack([classes, classes[::-1]])).to(DEV).contiguous()
+  ids = torch.full((n,), float(ci + 10), device=DEV)
+  scl = torch.full((n,), float(g['scale_%d' % ci][0]), device=DEV)
+  for mi, cfg in enumerate(methods):
+    det = torch.empty(n, 100, 7, device=DEV)
+    keep = torch.empty(n, 100, dtype=torch.int32, device=DEV)
+    valid = torch.empty(n, dtype=torch.int32, device=DEV)
+    ops.per_class_nms(b, s_, c, ids, scl, int(g['ncls_%d' % ci]), 100, cfg['method'],
+                      cfg['iou_thresh'], det, keep, valid)
+    torch.cuda.synchronize()
+    ref = g['out_%d_%d' % (ci, mi)]
+    got = det.cpu().numpy()
+    np.testing.assert_array_equal(got[0], ref, err_msg='case %d method %d' % (ci, mi))
+    np.testing.assert_array_equal(got[1], ref, err_msg='case %d method %d (reversed)' % (ci, mi))
+    nv = int((ref[:, 5] > -1e4).sum())
+    assert valid.cpu().tolist() == [nv, nv]
+    kp = keep.cpu().numpy()
+    # keep indices: the anchor each row came from (scores are distinct -> unique match)
+    np.testing.assert_array_equal(scores[kp[0, :nv]], ref[:nv, 5])
+    np.testing.assert_array_equal(kp[1, :nv], k - 1 - kp[0, :nv])
+    assert (kp[:, nv:] == -1).all()
+
+
+def test_per_class_nms_soft_methods_not_built():
+  ops = _ops()
+  z = torch.zeros(1, 8, 4, device=DEV)
+  with pytest.raises(Exception):
+    ops.per_class_nms(z, torch.zeros(1, 8, device=DEV), torch.zeros(1, 8, dtype=torch.int32, device=DEV),
+                      None, None, 90, 100, 'gaussian', None, torch.empty(1, 100, 7, device=DEV),
+                      torch.empty(1, 100, dtype=torch.int32, device=DEV),
+                      torch.empty(1, dtype=torch.int32, device=DEV))

@@ -51,3 +51,54 @@ def test_serving_driver_call_surface():
     driver.export('/tmp/x')
   with pytest.raises(ValueError):
     inference.ServingDriver('resnet50', '_')
+
+
+def test_generate_detections_per_class_path():
+  """postprocess.generate_detections (the reference's nms_configs.pyfunc branch) on an engine:
+  equals the oracle's per_class_nms on the engine's own pre-NMS output wherever the candidate
+  scores are distinct (NumPy leaves the order of equal scores undefined)."""
+  from automl_b200 import hparams_config, postprocess, weights
+  from automl_b200.arch import DetArch
+  from automl_b200.engine import Engine
+  c = hparams_config.get_efficientdet_config('efficientdet-d0')
+  c.override(dict(image_size=128))
+  c.nms_configs.method = 'hard'
+  c.nms_configs.pyfunc = True
+  eng = Engine(c, weights.synthetic_weights(DetArch(c), 3), 2)
+  x = np.random.default_rng(5).uniform(-2, 2, size=(2, 128, 128, 3)).astype(np.float32)
+  eng.forward(torch.from_numpy(x))
+  params = c.as_dict()
+  scales, ids = np.asarray([1.25, 2.0], np.float32), np.asarray([7, 8], np.float32)
+  det = postprocess.generate_detections(params, eng, scales, ids).cpu().numpy()
+  torch.cuda.synchronize()
+  assert det.shape == (2, 100, 7)
+  ps = eng.pre_nms_only()
+  boxes, scores, classes = (ps[k].cpu().numpy() for k in ('boxes', 'scores', 'classes'))
+  K = scores.shape[1]
+  for i in range(2):
+    assert (np.diff(det[i][:, 5]) <= 0).all()
+    assert set(np.unique(det[i][:, 0])) == {ids[i]}
+  # The engine's fp16 logits produce tied scores, whose order NumPy's argsort leaves undefined.
+  # Bit-exact check on the engine's boxes / classes with the scores replaced by distinct values
+  # of the same ranking (score descending, higher anchor index first = the device's tie rule).
+  ranked = np.empty_like(scores)
+  for i in range(2):
+    order = np.lexsort((np.arange(K), scores[i]))[::-1]
+    ranked[i, order] = (1.0 - np.arange(K) / K).astype(np.float32)
+  assert all(len(np.unique(ranked[i])) == K for i in range(2))
+  got, _, _ = postprocess.per_class_nms(ps['boxes'], torch.from_numpy(ranked).cuda(), ps['classes'],
+                                        ids, scales, params['num_classes'], 100, params['nms_configs'])
+  got = got.cpu().numpy()
+  for i in range(2):
+    ref = po.per_class_nms(boxes[i], ranked[i], classes[i], ids[i:i + 1], scales[i:i + 1],
+                           params['num_classes'], 100, params['nms_configs'])
+    np.testing.assert_array_equal(got[i], ref)
+    # same keep decisions on the real scores: same boxes and classes row by row
+    np.testing.assert_array_equal(det[i][:, [1, 2, 3, 4, 6]], ref[:, [1, 2, 3, 4, 6]])
+  # flip mirrors x about the original image width (postprocess.py:558-571)
+  flipped = postprocess.generate_detections(params, eng, scales, ids, flip=True).cpu().numpy()
+  ow = scales * 128
+  np.testing.assert_array_equal(flipped[..., 1], ow[:, None] - det[..., 3])
+  np.testing.assert_array_equal(flipped[..., 3], ow[:, None] - det[..., 1])
+  t = postprocess.transform_detections(torch.from_numpy(det)).numpy()
+  np.testing.assert_array_equal(t[..., 3], det[..., 3] - det[..., 1])
