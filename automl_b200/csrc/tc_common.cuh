@@ -54,6 +54,14 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
       "r"(src), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(map)),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -201,6 +209,37 @@ inline int make_map4(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1
     set_error("cuTensorMapEncodeTiled(4d) failed (%d) dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u]",
               static_cast<int>(r), (unsigned long long)d0, (unsigned long long)d1,
               (unsigned long long)d2, (unsigned long long)d3, box0, box1, box2);
+    return EDET_ERR_CUDA;
+  }
+  return EDET_OK;
+}
+
+// 4-D half tensor with explicit (element) strides for d1, d2, d3 (d0 contiguous): strided views
+// such as the (row parity, column parity) sub-images a stride-2 convolution reads.
+inline int make_map4_strided(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1,
+                             uint64_t d2, uint64_t d3, uint64_t s1, uint64_t s2, uint64_t s3,
+                             uint32_t box0, uint32_t box1, uint32_t box2) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return EDET_ERR_CUDA;
+  }
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {s1 * 2, s2 * 2, s3 * 2};
+  cuuint32_t box[4] = {box0, box1, box2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle swz = box0 == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : box0 == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                              : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d strided) failed (%d) dims=[%llu,%llu,%llu,%llu] "
+              "strides=[%llu,%llu,%llu] box=[%u,%u,%u]", static_cast<int>(r),
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+              (unsigned long long)d3, (unsigned long long)strides[0],
+              (unsigned long long)strides[1], (unsigned long long)strides[2], box0, box1, box2);
     return EDET_ERR_CUDA;
   }
   return EDET_OK;

@@ -75,6 +75,16 @@ def depthwise_conv(x, out, w, bias, act, k, stride, se_sum=None):
             n, h, wd, c, k, stride, act, _stream())
 
 
+def conv2d(x, wt, bias, out, act, ksize, stride, residual=None):
+  """k x k 'SAME' convolution on tcgen05: x fp16 [N,H,W,cin], wt fp16 [k*k, cout, cin], bias fp32
+  [cout], out fp16 [N,ceil(H/s),ceil(W/s),cout], residual like out or None."""
+  n, h, w, cin = x.shape
+  cout = wt.shape[1]
+  _lib.call('edet_conv2d', _ptr(x, torch.float16), _ptr(wt, torch.float16),
+            _ptr(bias, torch.float32), _ptr(residual, torch.float16), _ptr(out, torch.float16),
+            n, h, w, cin, cout, ksize, stride, act, _stream())
+
+
 def mbconv_expand_dw(x, we, bias_e, wd, bias_d, out, act, k, stride, se_sum=None):
   """Fused expand 1x1 + depthwise kxk: x fp16 [N,H,W,cin], we fp16 [cmid,cin], wd fp16
   [k*k,cmid], out fp16 [N,Ho,Wo,cmid]; se_sum int64 [N,cmid] (added to) or None."""

@@ -81,6 +81,18 @@ int edet_preprocess(const uint8_t* in, float* out, int n, int h, int w, int out_
 int edet_stem_conv(const float* in, edet_half* out, const edet_half* w, const float* bias,
                    int n, int h, int wd, int cout, int act, edet_stream_t stream);
 
+/* k x k convolution 'SAME' (ksize in {1,3,5}, stride in {1,2}) + bias (BN folded) + act
+ * (+ residual) as an implicit GEMM on tcgen05: the Fused-MBConv convolutions of EfficientNetV2.
+ * Replaces Conv2D k x k + BN (+ act) (+ skip)  efficientnetv2/effnetv2_model.py:331-341, 355-364,
+ * 387-404 (FusedMBConvBlock), residual :270-277.
+ *   in  half [n, h, w, cin]                 wt  half [ksize*ksize][cout][cin] (tap-major, cin
+ *   contiguous, BN scale folded)            bias float32 [cout]
+ *   residual half [n, ho, wo, cout] or NULL out half [n, ho, wo, cout], ho = ceil(h / stride)
+ *   cin % 8 == 0, cout % 8 == 0; act in {NONE, SWISH, RELU6}. */
+int edet_conv2d(const edet_half* in, const edet_half* wt, const float* bias,
+                const edet_half* residual, edet_half* out, int n, int h, int w, int cin, int cout,
+                int ksize, int stride, int act, edet_stream_t stream);
+
 /* Fused front half of an MBConv block: expand 1x1 + BN + act  ->  depthwise kxk 'SAME' + BN +
  * act (+ SE squeeze), the expanded [N,H,W,cmid] tensor never leaves the SM (tcgen05 accumulators
  * in TMEM -> fp16 tile in shared memory -> depthwise).  Same results as edet_pointwise_conv

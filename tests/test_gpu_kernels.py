@@ -244,6 +244,45 @@ def test_fuse_dw_all_modes():
     assert torch.allclose(out.cpu().double(), ref, rtol=2e-3, atol=2e-3), (h, w)
 
 
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, act, residual      (EfficientNetV2-S fused stages + edges)
+    (2, 24, 24, 24, 24, 3, 1, utils.ACT_SWISH, True),      # stage 0: single 3x3 conv + act + skip
+    (2, 24, 24, 24, 96, 3, 2, utils.ACT_SWISH, False),     # stage 1 first block: 3x3 s2 expand
+    (1, 17, 23, 48, 192, 3, 1, utils.ACT_SWISH, False),    # stage 1 repeat: odd sizes, N = 192
+    (1, 19, 13, 48, 192, 3, 2, utils.ACT_SWISH, False),    # stride 2 on odd sizes
+    (2, 12, 12, 64, 256, 3, 1, utils.ACT_SWISH, False),    # stage 2: N = 256 (one accum stage)
+    (1, 40, 56, 32, 32, 3, 1, utils.ACT_NONE, True),       # several tiles, 64B swizzle K
+    (1, 9, 9, 160, 320, 3, 1, utils.ACT_RELU6, False),     # 3 k-blocks x 9 taps, 3 N tiles
+    (1, 10, 14, 16, 40, 5, 2, utils.ACT_NONE, False),      # 5x5 stride 2
+    (3, 64, 64, 24, 24, 3, 1, utils.ACT_SWISH, True),      # persistent loop over many tiles
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv2d_tc(case):
+  ops = _ops()
+  n, h, w, cin, cout, k, s, act, has_res = case
+  g = torch.Generator().manual_seed(17 + h + cin + cout)
+  x = torch.randn(n, h, w, cin, generator=g).half()
+  wk = (torch.randn(k, k, cin, cout, generator=g) / (k * cin**0.5)).half()     # HWIO like Keras
+  bias = torch.randn(cout, generator=g) * 0.1
+  ho, wo = -(-h // s), -(-w // s)
+  res = torch.randn(n, ho, wo, cout, generator=g).half() if has_res else None
+  out = torch.full((n, ho, wo, cout), 7.0, dtype=torch.float16, device=DEV)
+  wt = wk.permute(0, 1, 3, 2).reshape(k * k, cout, cin).contiguous()            # [tap][cout][cin]
+  ops.conv2d(x.to(DEV), wt.to(DEV), bias.to(DEV), out, act, k, s,
+             residual=res.to(DEV) if has_res else None)
+  torch.cuda.synchronize()
+  ref = eo.conv2d_same(x.double().permute(0, 3, 1, 2), wk.double(), s) + bias.double().view(1, -1, 1, 1)
+  ref = act_ref(ref, act).permute(0, 2, 3, 1)
+  if has_res:
+    ref = ref + res.double()
+  got = out.cpu().double()
+  assert got.shape == ref.shape
+  assert rel_l2(got, ref) < 6e-4, rel_l2(got, ref)
+  assert torch.allclose(got, ref, rtol=4e-3, atol=4e-3), float((got - ref).abs().max())
+
+
 SEP_CASES = [
     # n, (h, w), c, nout, pre, post, inputs [(mode, (h, w))]
     (2, (20, 20), 64, 64, utils.ACT_SWISH, utils.ACT_NONE, ['same', 'up']),        # td node
