@@ -11,27 +11,39 @@ namespace edet {
 constexpr int kFuseThreads = 256;
 constexpr int kFuseTH = 8, kFuseTW = 16;   // output tile
 constexpr int kFuseCB = 32;                // channels per CTA
+// smem pixel pitch of the fused tile: 36 floats = 9 x 16 bytes.  An ODD number of 16-byte units
+// makes both the phase-1 stores (lanes = 4 channel groups x 2 pixels per quarter warp) and the
+// phase-2 loads (4 channel groups x 2 columns) hit 8 distinct bank groups.
+constexpr int kFusePitch = kFuseCB + 4;
+
 template <int ACT>
 __global__ void __launch_bounds__(kFuseThreads)
 fuse_dw_kernel(const FuseParams p, const __half* __restrict__ dw_w, __half* __restrict__ out,
                int h, int wd, int c, int chunks) {
   pdl_launch_dependents();
-  pdl_wait_prior();
   constexpr int HT = kFuseTH + 2, WT = kFuseTW + 2, G = kFuseCB / 8;
-  __shared__ __align__(16) float fused[HT * WT][kFuseCB];
+  static_assert(G == 4 && kFuseTH * kFuseTW * G == 2 * kFuseThreads, "phase-2 mapping");
+  __shared__ __align__(16) float fused[HT * WT * kFusePitch];
+  __shared__ __align__(16) float wsm[9 * kFuseCB];
   const int n = blockIdx.z / chunks;
   const int c0 = (blockIdx.z % chunks) * kFuseCB;
   const int y0 = blockIdx.y * kFuseTH, x0 = blockIdx.x * kFuseTW;
   const int groups = min(G, (c - c0) >> 3);
+  // depthwise weights of this channel chunk as fp32 (constants: fetched before the PDL wait)
+  for (int i = threadIdx.x; i < 9 * kFuseCB; i += kFuseThreads) {
+    const int tap = i / kFuseCB, ch = i % kFuseCB;
+    wsm[i] = (c0 + ch < c) ? __half2float(__ldg(dw_w + static_cast<size_t>(tap) * c + c0 + ch)) : 0.f;
+  }
+  pdl_wait_prior();
 
   // ---- phase 1: fused + activated map for the tile and its 1-pixel halo -------------------
   for (int item = threadIdx.x; item < HT * WT * G; item += kFuseThreads) {
-    const int g = item % G, pix = item / G;
-    const int ty = pix / WT, tx = pix % WT;
+    const int g = item & (G - 1), pix = item >> 2;
+    const int ty = pix / WT, tx = pix - ty * WT;
     const int y = y0 + ty - 1, x = x0 + tx - 1;
-    float acc[8];
+    float2 acc[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int e = 0; e < 4; ++e) acc[e] = make_float2(0.f, 0.f);
     if (g < groups && y >= 0 && y < h && x >= 0 && x < wd) {
       const int ch = c0 + g * 8;
       for (int i = 0; i < p.n_inputs; ++i) {
@@ -39,48 +51,63 @@ fuse_dw_kernel(const FuseParams p, const __half* __restrict__ dw_w, __half* __re
         const __half* base = fi.ptr + static_cast<size_t>(n) * fi.h * fi.w * c;
         float v[8];
         resample8(fi, base, c, y, x, ch, v);
+        const float2 w2 = make_float2(fi.weight, fi.weight);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], fi.weight, acc[e]);
+        for (int e = 0; e < 4; ++e) acc[e] = __ffma2_rn(make_float2(v[2 * e], v[2 * e + 1]), w2, acc[e]);
       }
-#pragma unroll
-      for (int e = 0; e < 8; e += 4) {
-        float2 a = make_float2(acc[e], acc[e + 1]), b = make_float2(acc[e + 2], acc[e + 3]);
-        apply_act4<ACT>(a, b);
-        acc[e] = a.x; acc[e + 1] = a.y; acc[e + 2] = b.x; acc[e + 3] = b.y;
-      }
+      apply_act4<ACT>(acc[0], acc[1]);
+      apply_act4<ACT>(acc[2], acc[3]);
     }
-    float4* dst = reinterpret_cast<float4*>(&fused[pix][g * 8]);
-    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    float4* dst = reinterpret_cast<float4*>(fused + pix * kFusePitch + g * 8);
+    dst[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+    dst[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
   }
   __syncthreads();
 
-  // ---- phase 2: depthwise 3x3 over the shared fused map -----------------------------------
-  for (int item = threadIdx.x; item < kFuseTH * kFuseTW * G; item += kFuseThreads) {
-    const int g = item % G, pix = item / G;
-    const int ty = pix / kFuseTW, tx = pix % kFuseTW;
-    const int y = y0 + ty, x = x0 + tx;
-    if (g >= groups || y >= h || x >= wd) continue;
-    const int ch = c0 + g * 8;
-    float acc[8];
+  // ---- phase 2: depthwise 3x3, one thread = 8 channels x 2 vertically adjacent pixels --------
+  {
+    const int g = threadIdx.x & (G - 1);
+    const int tx = (threadIdx.x >> 2) & (kFuseTW - 1);
+    const int ty = (threadIdx.x >> 6) * 2;            // rows ty, ty + 1
+    const int x = x0 + tx;
+    if (g >= groups || x >= wd || y0 + ty >= h) return;
+    float2 acc[2][4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int r = 0; r < 2; ++r)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
+      for (int e = 0; e < 4; ++e) acc[r][e] = make_float2(0.f, 0.f);
+    // taps in (ky, kx) order for each output row, so the sums match the scalar fmaf chain
+#pragma unroll
+    for (int iy = 0; iy < 4; ++iy) {
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        float wf[8];
-        half8_to_float(__ldg(reinterpret_cast<const uint4*>(dw_w + static_cast<size_t>(ky * 3 + kx) * c + ch)), wf);
-        const float4* src = reinterpret_cast<const float4*>(&fused[(ty + ky) * WT + tx + kx][g * 8]);
+        const float4* src = reinterpret_cast<const float4*>(fused + ((ty + iy) * WT + tx + kx) * kFusePitch + g * 8);
         const float4 a = src[0], b = src[1];
-        acc[0] = fmaf(a.x, wf[0], acc[0]); acc[1] = fmaf(a.y, wf[1], acc[1]);
-        acc[2] = fmaf(a.z, wf[2], acc[2]); acc[3] = fmaf(a.w, wf[3], acc[3]);
-        acc[4] = fmaf(b.x, wf[4], acc[4]); acc[5] = fmaf(b.y, wf[5], acc[5]);
-        acc[6] = fmaf(b.z, wf[6], acc[6]); acc[7] = fmaf(b.w, wf[7], acc[7]);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int ky = iy - r;
+          if (ky >= 0 && ky < 3) {
+            const float4* wp = reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * kFuseCB + g * 8);
+            const float4 w0 = wp[0], w1 = wp[1];
+            acc[r][0] = __ffma2_rn(make_float2(a.x, a.y), make_float2(w0.x, w0.y), acc[r][0]);
+            acc[r][1] = __ffma2_rn(make_float2(a.z, a.w), make_float2(w0.z, w0.w), acc[r][1]);
+            acc[r][2] = __ffma2_rn(make_float2(b.x, b.y), make_float2(w1.x, w1.y), acc[r][2]);
+            acc[r][3] = __ffma2_rn(make_float2(b.z, b.w), make_float2(w1.z, w1.w), acc[r][3]);
+          }
+        }
       }
     }
-    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * h + y) * wd + x) * c + ch) =
-        float_to_half8(acc);
+    const int ch = c0 + g * 8;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int y = y0 + ty + r;
+      if (y < h) {
+        const float o[8] = {acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y,
+                            acc[r][2].x, acc[r][2].y, acc[r][3].x, acc[r][3].y};
+        *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * h + y) * wd + x) * c + ch) =
+            float_to_half8(o);
+      }
+    }
   }
 }
 
