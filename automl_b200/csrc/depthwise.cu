@@ -16,7 +16,7 @@ constexpr double kSeFixedScale = 1048576.0;  // 2^20: fixed-point scale of the S
 
 template <int K, int S>
 struct DwCfg {
-  static constexpr int ROWS = (S == 2) ? 4 : 8;             // output rows per thread
+  static constexpr int ROWS = (S == 2 || K == 5) ? 4 : 8;   // output rows per thread
   static constexpr int IN_ROWS = (ROWS - 1) * S + K;        // input rows touched
   static constexpr int IN_COLS = (kDwTW - 1) * S + K;       // input columns touched
 };
@@ -28,7 +28,7 @@ struct DwCfg {
 // needs 25 MACs per output element, more than the scalar FFMA pipe can issue at the HBM rate,
 // and without the column tiling the half->float conversions of the kx re-reads dominate.
 template <int K, int S, int ACT, bool HAS_BIAS, bool HAS_SE>
-__global__ void __launch_bounds__(kDwThreads, (K == 3) ? 4 : 3)
+__global__ void __launch_bounds__(kDwThreads, (K == 3 || S == 1) ? 4 : 3)
 depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
                  const __half* __restrict__ w, const float* __restrict__ bias,
                  long long* __restrict__ se_sum, int h, int wd, int c, int ho, int wo, int pad_t,
