@@ -61,8 +61,8 @@ SIGNATURES = {
                             c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_void_p]),
     'edet_per_class_nms': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                   c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
-                                   c_void_p]),
+                                   c_int, c_int, c_int, c_float, c_float, c_float, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -1,4 +1,4 @@
-// CUDA replacement for nms_np.per_class_nms (hard and DIoU NMS), the numpy post-process the
+// CUDA replacement for nms_np.per_class_nms (hard / DIoU NMS here, the soft methods further down), the numpy post-process the
 // reference calls through tf.numpy_function (tf2/postprocess.py:541-556, nms_np.py:28-126,
 // 220-264): per class, greedy NMS in descending score order with the "+1 pixel" float32 IoU, all
 // survivors of all classes merged, the top max_boxes by score emitted as
@@ -255,14 +255,152 @@ per_class_nms_kernel(const float* __restrict__ boxes, const float* __restrict__ 
   if (tid == 0) num_valid[n] = nkept;
 }
 
+// ---- soft NMS (nms_np.py:129-191: gaussian / linear) -------------------------------------------
+// nms_np's per-class loop -- arg-max of the decayed scores, decay every other box of the class by
+// exp(-iou^2 / sigma) (gaussian) or 1 - iou where iou > iou_thresh (linear), drop boxes whose
+// score falls below score_thresh -- emits each class's boxes in non-increasing score order, and
+// classes do not interact.  The merged top max_boxes are therefore the first max_boxes GLOBAL
+// arg-max selections: one pass over the K current scores per selection (decay of the winner's
+// class fused with the arg-max for the next selection), max_boxes selections in all.
+//   cur: float32 [n][k] workspace holding the current (decayed) scores, -inf = removed.
+// Equal scores: the lower anchor index is selected first.  gaussian: exp is evaluated in double
+// and rounded to float32; NumPy's SIMD float32 exp is within 2 ulp of that, so scores can differ
+// from a given NumPy build in the last bits (the linear method is bit-identical).
+constexpr int kSoftThreads = 512;
+
+struct SoftSmem {
+  float4 kbox[kMaxKeep];
+  float kscore[kMaxKeep];
+  int kcls[kMaxKeep];
+  int kidx[kMaxKeep];
+  float red_v[kSoftThreads / 32];
+  int red_i[kSoftThreads / 32];
+  float win_v;
+  int win_i;
+};
+
+template <int METHOD>
+__global__ void __launch_bounds__(kSoftThreads)
+per_class_soft_nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                          const int32_t* __restrict__ classes, const float* __restrict__ image_ids,
+                          const float* __restrict__ image_scales, int k, int num_classes,
+                          int max_boxes, float iou_thresh, float sigma, float score_thresh,
+                          float* __restrict__ cur_all, float* __restrict__ detections,
+                          int32_t* __restrict__ keep_index, int32_t* __restrict__ num_valid) {
+  __shared__ SoftSmem sm;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float4* bx = reinterpret_cast<const float4*>(boxes) + static_cast<size_t>(n) * k;
+  const float* sc = scores + static_cast<size_t>(n) * k;
+  const int32_t* cl = classes + static_cast<size_t>(n) * k;
+  float* cur = cur_all + static_cast<size_t>(n) * k;
+  const float kNegInf = __int_as_float(0xff800000);
+
+  float4 wbox = make_float4(0.f, 0.f, 0.f, 0.f);
+  float warea = 0.f;
+  int wcls = -1, widx = -1, nkept = 0;
+  for (int t = 0; t < max_boxes; ++t) {
+    // one pass: (t > 0) decay the class of the previous winner; always: arg-max of what remains.
+    // Element i is always handled by thread i % kSoftThreads, so `cur` needs no global ordering.
+    float best_v = kNegInf;
+    int best_i = 0x7fffffff;
+    for (int i = tid; i < k; i += kSoftThreads) {
+      float v;
+      if (t == 0) {
+        const int c = cl[i];
+        v = (c >= 0 && c < num_classes) ? sc[i] : kNegInf;
+        cur[i] = v;
+      } else {
+        v = cur[i];
+        if (i == widx) {
+          v = kNegInf;
+          cur[i] = v;
+        } else if (v != kNegInf && cl[i] == wcls) {
+          const float4 r = bx[i];
+          const float4 b = make_float4(r.y, r.x, r.w, r.z);
+          const float iou = metric<false>(wbox, warea, b, area_plus1(b));
+          float wgt = 1.0f;
+          if (METHOD == EDET_NMS_LINEAR) {
+            if (iou > iou_thresh) wgt = __fsub_rn(1.0f, iou);
+          } else {
+            const float e = -__fdiv_rn(__fmul_rn(iou, iou), sigma);
+            wgt = static_cast<float>(exp(static_cast<double>(e)));
+          }
+          v = __fmul_rn(v, wgt);
+          if (!(v >= score_thresh)) v = kNegInf;
+          cur[i] = v;
+        }
+      }
+      if (v > best_v) { best_v = v; best_i = i; }   // ascending i: ties keep the lower index
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+    }
+    if (lane == 0) { sm.red_v[warp] = best_v; sm.red_i[warp] = best_i; }
+    __syncthreads();
+    if (warp == 0) {
+      float v = lane < kSoftThreads / 32 ? sm.red_v[lane] : kNegInf;
+      int i = lane < kSoftThreads / 32 ? sm.red_i[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+      }
+      if (lane == 0) { sm.win_v = v; sm.win_i = i; }
+    }
+    __syncthreads();
+    const float wv = sm.win_v;
+    widx = sm.win_i;
+    if (wv == kNegInf) break;     // nothing left
+    const float4 r = bx[widx];
+    wbox = make_float4(r.y, r.x, r.w, r.z);
+    warea = area_plus1(wbox);
+    wcls = cl[widx];
+    if (tid == 0) {
+      sm.kbox[nkept] = wbox;
+      sm.kscore[nkept] = wv;
+      sm.kcls[nkept] = wcls;
+      sm.kidx[nkept] = widx;
+    }
+    ++nkept;
+    __syncthreads();              // red_v / win_* are rewritten by the next selection
+  }
+  __syncthreads();
+  const float id = image_ids ? image_ids[n] : static_cast<float>(n);
+  const float scale = image_scales ? image_scales[n] : 1.0f;
+  for (int i = tid; i < max_boxes; i += kSoftThreads) {
+    float* d = detections + (static_cast<size_t>(n) * max_boxes + i) * 7;
+    if (i < nkept) {
+      const float4 b = sm.kbox[i];
+      d[0] = id;
+      d[1] = __fmul_rn(b.x, scale); d[2] = __fmul_rn(b.y, scale);
+      d[3] = __fmul_rn(b.z, scale); d[4] = __fmul_rn(b.w, scale);
+      d[5] = sm.kscore[i];
+      d[6] = static_cast<float>(sm.kcls[i] + 1);
+      keep_index[static_cast<size_t>(n) * max_boxes + i] = sm.kidx[i];
+    } else {
+      d[0] = id;
+      d[1] = __fmul_rn(0.f, scale); d[2] = d[1]; d[3] = d[1]; d[4] = d[1];
+      d[5] = kDummyScore;
+      d[6] = 0.f;
+      keep_index[static_cast<size_t>(n) * max_boxes + i] = -1;
+    }
+  }
+  if (tid == 0) num_valid[n] = nkept;
+}
+
 }  // namespace pcn
 }  // namespace edet
 
 extern "C" int edet_per_class_nms(const float* boxes, const float* scores, const int32_t* classes,
                                   const float* image_ids, const float* image_scales, int n, int k,
                                   int num_classes, int max_boxes_to_draw, int method,
-                                  float iou_thresh, float* detections, int32_t* keep_index,
-                                  int32_t* num_valid, edet_stream_t stream) {
+                                  float iou_thresh, float sigma, float score_thresh, float* work,
+                                  float* detections, int32_t* keep_index, int32_t* num_valid,
+                                  edet_stream_t stream) {
   using namespace edet;
   using namespace edet::pcn;
   EDET_CHECK_ARG(boxes && scores && classes && detections && keep_index && num_valid,
@@ -271,10 +409,24 @@ extern "C" int edet_per_class_nms(const float* boxes, const float* scores, const
   EDET_CHECK_ARG(max_boxes_to_draw > 0 && max_boxes_to_draw <= kMaxKeep,
                  "per_class_nms: max_boxes_to_draw must be in 1..%d (got %d)", kMaxKeep,
                  max_boxes_to_draw);
+  cudaStream_t s = as_stream(stream);
+  if (method == EDET_NMS_GAUSSIAN || method == EDET_NMS_LINEAR) {
+    EDET_CHECK_ARG(work != nullptr, "per_class_nms: the soft methods need the [n][k] float workspace");
+    EDET_CHECK_ARG(sigma > 0.f, "per_class_nms: sigma must be positive");
+    if (method == EDET_NMS_GAUSSIAN)
+      per_class_soft_nms_kernel<EDET_NMS_GAUSSIAN><<<n, kSoftThreads, 0, s>>>(
+          boxes, scores, classes, image_ids, image_scales, k, num_classes, max_boxes_to_draw,
+          iou_thresh, sigma, score_thresh, work, detections, keep_index, num_valid);
+    else
+      per_class_soft_nms_kernel<EDET_NMS_LINEAR><<<n, kSoftThreads, 0, s>>>(
+          boxes, scores, classes, image_ids, image_scales, k, num_classes, max_boxes_to_draw,
+          iou_thresh, sigma, score_thresh, work, detections, keep_index, num_valid);
+    EDET_CHECK_LAUNCH();
+    return EDET_OK;
+  }
   if (method != EDET_NMS_HARD && method != EDET_NMS_DIOU) {
-    set_error("per_class_nms: method %d is not built (hard and diou are; the soft methods of "
-              "nms_np.py:129-191 are not)", method);
-    return EDET_ERR_UNSUPPORTED;
+    set_error("per_class_nms: unknown method %d", method);
+    return EDET_ERR_INVALID;
   }
   static bool configured = false;
   if (!configured) {
@@ -286,7 +438,6 @@ extern "C" int edet_per_class_nms(const float* boxes, const float* scores, const
                                          static_cast<int>(sizeof(Smem))));
     configured = true;
   }
-  cudaStream_t s = as_stream(stream);
   if (method == EDET_NMS_DIOU)
     per_class_nms_kernel<true><<<n, kThreads, sizeof(Smem), s>>>(
         boxes, scores, classes, image_ids, image_scales, k, num_classes, max_boxes_to_draw,

@@ -193,17 +193,26 @@ NMS_METHODS = {'hard': _lib.NMS_HARD, '': _lib.NMS_HARD, None: _lib.NMS_HARD, 'd
 
 
 def per_class_nms(boxes, scores, classes, image_ids, image_scales, num_classes, max_boxes_to_draw,
-                  method, iou_thresh, detections, keep_index, num_valid):
-  """nms_np.per_class_nms on the device (hard / diou): boxes fp32 [N,K,4] (ymin,xmin,ymax,xmax),
-  scores fp32 [N,K], classes i32 [N,K], image_ids / image_scales fp32 [N] or None ->
-  detections fp32 [N,max_boxes,7], keep_index i32 [N,max_boxes], num_valid i32 [N]."""
+                  method, iou_thresh, detections, keep_index, num_valid, sigma=None,
+                  score_thresh=None, work=None):
+  """nms_np.per_class_nms on the device: boxes fp32 [N,K,4] (ymin,xmin,ymax,xmax), scores fp32
+  [N,K], classes i32 [N,K], image_ids / image_scales fp32 [N] or None -> detections fp32
+  [N,max_boxes,7], keep_index i32 [N,max_boxes], num_valid i32 [N].  None / 0 thresholds take
+  nms_np's defaults (`x or default`, nms_np.py:43, 100, 148-150); the soft methods need `work`,
+  a float32 [N,K] workspace (allocated here when not given)."""
   n, k = scores.shape
   if method not in NMS_METHODS:
     raise ValueError('Unknown NMS method: {}'.format(method))
-  # nms_np: `iou_thresh or 0.5` (hard / diou), compared in float32
-  thr = float(iou_thresh) if iou_thresh else 0.5
+  code = NMS_METHODS[method]
+  soft = code in (_lib.NMS_GAUSSIAN, _lib.NMS_LINEAR)
+  thr = float(iou_thresh) if iou_thresh else (0.3 if soft else 0.5)
+  sig = float(sigma) if sigma else 0.5
+  sth = float(score_thresh) if score_thresh else 0.001
+  if soft and work is None:
+    work = torch.empty(n, k, dtype=torch.float32, device=scores.device)
   _lib.call('edet_per_class_nms', _ptr(boxes, torch.float32), _ptr(scores, torch.float32),
             _ptr(classes, torch.int32), _ptr(image_ids, torch.float32),
-            _ptr(image_scales, torch.float32), n, k, num_classes, max_boxes_to_draw,
-            NMS_METHODS[method], ctypes.c_float(thr), _ptr(detections, torch.float32),
+            _ptr(image_scales, torch.float32), n, k, num_classes, max_boxes_to_draw, code,
+            ctypes.c_float(thr), ctypes.c_float(sig), ctypes.c_float(sth),
+            _ptr(work, torch.float32), _ptr(detections, torch.float32),
             _ptr(keep_index, torch.int32), _ptr(num_valid, torch.int32), _stream())

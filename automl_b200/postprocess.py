@@ -8,8 +8,9 @@
       class] (the layout of nms_np, NOT the [id, y, x, y, x, ...] layout of det_post_process).
   transform_detections(detections)   postprocess.py:589-601 -> [id, x, y, w, h, score, class]
 
-Only the `hard` and `diou` methods of nms_np run on the device; `gaussian` / `linear` raise
-NotImplementedError (the default serving path, NMS-V5 gaussian, is Engine.detect()).
+All four methods of nms_np run on the device (`hard`, `diou`: rows bit-identical to NumPy;
+`linear`: bit-identical; `gaussian`: identical selections, scores within a few float32 ulp because
+NumPy's SIMD exp is not correctly rounded).  The default serving path (NMS-V5) is Engine.detect().
 """
 import torch
 
@@ -21,8 +22,6 @@ def per_class_nms(boxes, scores, classes, image_ids, image_scales, num_classes, 
                   nms_configs):
   """Batched nms_np.per_class_nms on device tensors; returns (detections, keep_index, num_valid)."""
   method = nms_configs['method']
-  if method in ('gaussian', 'linear'):
-    raise NotImplementedError('nms_np soft NMS (%s) is not built on the device yet' % method)
   n = scores.shape[0]
   dev = scores.device
   det = torch.empty(n, max_boxes_to_draw, 7, dtype=torch.float32, device=dev)
@@ -30,7 +29,8 @@ def per_class_nms(boxes, scores, classes, image_ids, image_scales, num_classes, 
   valid = torch.empty(n, dtype=torch.int32, device=dev)
   as_f32 = lambda v: None if v is None else torch.as_tensor(v, dtype=torch.float32).to(dev).contiguous()
   ops.per_class_nms(boxes, scores, classes, as_f32(image_ids), as_f32(image_scales), num_classes,
-                    max_boxes_to_draw, method, nms_configs.get('iou_thresh'), det, keep, valid)
+                    max_boxes_to_draw, method, nms_configs.get('iou_thresh'), det, keep, valid,
+                    sigma=nms_configs.get('sigma'), score_thresh=nms_configs.get('score_thresh'))
   return det, keep, valid
 
 

@@ -243,8 +243,14 @@ int edet_nms_v5(const float* boxes, const float* scores, const int32_t* classes,
  *   class + 1], boxes x image_scale; rows beyond the survivors are [image_id, 0,0,0,0, -1e5, 0]
  *   keep_index int32 [n, max_boxes_to_draw]: anchor index of each row (-1 for dummy rows)
  *   num_valid int32 [n]
- * Equal scores: the higher anchor index first (NumPy's unstable argsort leaves this undefined).
- * EDET_NMS_GAUSSIAN / EDET_NMS_LINEAR return EDET_ERR_UNSUPPORTED (not built yet).
+ * hard / diou: equal scores -> the higher anchor index first (NumPy's unstable argsort leaves this
+ * undefined).
+ * EDET_NMS_GAUSSIAN / EDET_NMS_LINEAR: soft NMS (nms_np.py:129-191) with `sigma` (gaussian),
+ * `iou_thresh` (linear) and `score_thresh` (nms_np's defaults 0.5 / 0.3 / 0.001 are applied by the
+ * caller); `work` is a float32 [n][k] workspace (may be NULL for hard / diou).  linear is
+ * bit-identical to NumPy; gaussian evaluates exp in double and rounds to float32, NumPy's SIMD
+ * float32 exp is within 2 ulp of that, so scores may differ in the last bits.  Equal scores ->
+ * the lower anchor index first.
  */
 #define EDET_NMS_HARD 0
 #define EDET_NMS_DIOU 1
@@ -253,8 +259,8 @@ int edet_nms_v5(const float* boxes, const float* scores, const int32_t* classes,
 int edet_per_class_nms(const float* boxes, const float* scores, const int32_t* classes,
                        const float* image_ids, const float* image_scales, int n, int k,
                        int num_classes, int max_boxes_to_draw, int method, float iou_thresh,
-                       float* detections, int32_t* keep_index, int32_t* num_valid,
-                       edet_stream_t stream);
+                       float sigma, float score_thresh, float* work, float* detections,
+                       int32_t* keep_index, int32_t* num_valid, edet_stream_t stream);
 
 #ifdef __cplusplus
 }

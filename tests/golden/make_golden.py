@@ -123,6 +123,33 @@ def main():
   hd['methods'] = np.asarray([json.dumps(m) for m in hd_methods])
   np.savez_compressed(os.path.join(OUT, 'nms_np_per_class_hard.npz'), **hd)
 
+  # per_class_nms goldens for the soft methods (gaussian: NumPy's float32 exp is within 2 ulp of
+  # the correctly rounded value and differs between CPUs, so the device is held to identical
+  # indices / boxes / classes and scores within a few ulp; linear has no transcendental: bit-exact)
+  rng3 = np.random.default_rng(9107)
+  sf = {}
+  sf_cases = [(50, 90, None), (600, 90, 15), (5000, 90, 125), (20000, 90, 400), (6000, 3, 40),
+              (3000, 1, -8), (49104, 90, -300)]
+  sf_methods = [dict(method='gaussian', iou_thresh=None, sigma=None, score_thresh=None),
+                dict(method='gaussian', iou_thresh=None, sigma=0.3, score_thresh=0.05),
+                dict(method='linear', iou_thresh=None, sigma=None, score_thresh=None),
+                dict(method='linear', iou_thresh=0.5, sigma=None, score_thresh=0.01)]
+  for ci, (k, ncls, clusters) in enumerate(sf_cases):
+    d = make_dets(rng3, k, clusters=clusters) if clusters is None or clusters > 0 else \
+        make_dense_dets(rng3, k, -clusters)
+    boxes = d[:, [1, 0, 3, 2]].copy()
+    scores = d[:, 4].copy()
+    classes = rng3.integers(0, ncls, size=k).astype(np.int32)
+    scale = np.asarray([0.5 + 0.25 * ci], np.float32)
+    for mi, cfg in enumerate(sf_methods):
+      cfg = dict(cfg, max_output_size=100, pyfunc=True, max_nms_inputs=0)
+      sf['out_%d_%d' % (ci, mi)] = nms_np.per_class_nms(
+          boxes, scores, classes, np.asarray([ci + 20], np.float32), scale, ncls, 100, cfg)
+    sf['boxes_%d' % ci], sf['scores_%d' % ci], sf['classes_%d' % ci] = boxes, scores, classes
+    sf['scale_%d' % ci], sf['ncls_%d' % ci] = scale, np.asarray(ncls)
+  sf['methods'] = np.asarray([json.dumps(m) for m in sf_methods])
+  np.savez_compressed(os.path.join(OUT, 'nms_np_per_class_soft.npz'), **sf)
+
   # ---- registry / fpn goldens ---------------------------------------------------------
   reg = {}
   names = (list(hparams_config.efficientdet_model_param_dict) +

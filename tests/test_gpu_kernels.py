@@ -537,11 +537,50 @@ def test_per_class_nms_matches_reference_module(ci):
     assert (kp[:, nv:] == -1).all()
 
 
-def test_per_class_nms_soft_methods_not_built():
+@pytest.mark.parametrize('ci', range(7))
+def test_per_class_soft_nms_matches_reference_module(ci):
+  """gaussian / linear soft NMS of nms_np.per_class_nms (tests/golden/nms_np_per_class_soft.npz,
+  written by the real module): `linear` rows are bit-identical; `gaussian` selects the same
+  anchors in the same order with the same boxes and classes, and its scores agree to 1e-6
+  relative (NumPy's float32 exp is not correctly rounded, the device's is)."""
+  import json
+  import os
+  ops = _ops()
+  g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'nms_np_per_class_soft.npz'))
+  methods = [json.loads(m) for m in g['methods']]
+  boxes, scores, classes = g['boxes_%d' % ci], g['scores_%d' % ci], g['classes_%d' % ci]
+  b = torch.from_numpy(boxes[None]).to(DEV).contiguous()
+  s_ = torch.from_numpy(scores[None]).to(DEV).contiguous()
+  c = torch.from_numpy(classes[None]).to(DEV).contiguous()
+  ids = torch.full((1,), float(ci + 20), device=DEV)
+  scl = torch.full((1,), float(g['scale_%d' % ci][0]), device=DEV)
+  for mi, cfg in enumerate(methods):
+    det = torch.empty(1, 100, 7, device=DEV)
+    keep = torch.empty(1, 100, dtype=torch.int32, device=DEV)
+    valid = torch.empty(1, dtype=torch.int32, device=DEV)
+    ops.per_class_nms(b, s_, c, ids, scl, int(g['ncls_%d' % ci]), 100, cfg['method'],
+                      cfg['iou_thresh'], det, keep, valid, sigma=cfg['sigma'],
+                      score_thresh=cfg['score_thresh'])
+    torch.cuda.synchronize()
+    ref = g['out_%d_%d' % (ci, mi)]
+    got = det.cpu().numpy()[0]
+    nv = int((ref[:, 5] > -1e4).sum())
+    assert int(valid.item()) == nv, (ci, mi)
+    if cfg['method'] == 'linear':
+      np.testing.assert_array_equal(got, ref, err_msg='case %d method %d' % (ci, mi))
+    else:
+      np.testing.assert_array_equal(got[:, [0, 1, 2, 3, 4, 6]], ref[:, [0, 1, 2, 3, 4, 6]])
+      np.testing.assert_allclose(got[:, 5], ref[:, 5], rtol=1e-6, atol=0)
+    kp = keep.cpu().numpy()[0]
+    np.testing.assert_array_equal(boxes[kp[:nv]][:, [1, 0, 3, 2]] * g['scale_%d' % ci][0], ref[:nv, 1:5])
+    assert (kp[nv:] == -1).all()
+
+
+def test_per_class_nms_bad_method():
   ops = _ops()
   z = torch.zeros(1, 8, 4, device=DEV)
-  with pytest.raises(Exception):
+  with pytest.raises(ValueError):
     ops.per_class_nms(z, torch.zeros(1, 8, device=DEV), torch.zeros(1, 8, dtype=torch.int32, device=DEV),
-                      None, None, 90, 100, 'gaussian', None, torch.empty(1, 100, 7, device=DEV),
+                      None, None, 90, 100, 'median', None, torch.empty(1, 100, 7, device=DEV),
                       torch.empty(1, 100, dtype=torch.int32, device=DEV),
                       torch.empty(1, dtype=torch.int32, device=DEV))
