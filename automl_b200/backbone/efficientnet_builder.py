@@ -225,15 +225,20 @@ def expand_blocks(blocks_args, global_params):
     dw_bn = bn_name()
     has_se = (global_params.use_se and se_ratio is not None and
               0 < se_ratio <= 1)
+    # Keras layers infer their input width from the tensor they get: with fix_head_stem (lite)
+    # the stem stays at 32 filters while blocks_args[0].input_filters is width-scaled (40 for
+    # lite3, 48 for lite4), so the first block's convs are built on the STEM's channel count
+    # (efficientnet_model.py:512-513 vs :652-653; parameter pins efficientdet_arch_test.py:104-114).
+    actual_in = stem_filters if idx == 0 else cin
     specs.append(
         BlockSpec(
             name='blocks_%d' % idx,
             kernel_size=k,
             stride=s,
-            input_filters=cin,
+            input_filters=actual_in,
             output_filters=cout,
             expand_ratio=e,
-            mid_filters=cin * e,
+            mid_filters=actual_in if e == 1 else cin * e,
             se_filters=max(1, int(cin * se_ratio)) if has_se else 0,
             has_skip=bool(id_skip and s == 1 and cin == cout),
             expand_name=expand_name,

@@ -94,6 +94,24 @@ def test_network_parity_baseline_configs(name, size, bb_tol, head_tol):
     assert rel_l2(box_out[l].float().cpu(), box_ref[l]) < head_tol, 'box %d' % l
 
 
+def test_network_parity_lite3():
+  """A lite model end to end: relu6, no SE, `sum` fusion, and the fix_head_stem case where the
+  first block is built on the stem's 32 channels although its block args say 40."""
+  c, a, w, x = _setup('efficientdet-lite3', 128, 1, seed=5)
+  assert a.blocks[0].input_filters == 32 and a.blocks[0].mid_filters == 32
+  orc = eo.Oracle(c, w, torch.float32)
+  cls_ref, box_ref = orc(x)
+  eng = _engine(c, w, 1, use_cuda_graph=False)
+  cls_out, box_out = eng.forward(torch.from_numpy(x))
+  torch.cuda.synchronize()
+  for b in a.blocks:
+    got = eng.buffers[b.name + '/out'].float().cpu().permute(0, 3, 1, 2)
+    assert rel_l2(got, orc.endpoints[b.name]) < REL_TOL, b.name
+  for l in a.levels:
+    assert rel_l2(cls_out[l].float().cpu(), cls_ref[l]) < REL_TOL
+    assert rel_l2(box_out[l].float().cpu(), box_ref[l]) < 2.5e-3      # `sum` fusion bar (see below)
+
+
 def test_network_parity_d1_relu6():
   """A second backbone (b1) with the lite activation (relu6)."""
   c, a, w, x = _setup('efficientdet-d1', 128, 1, seed=3, act_type='relu6')
