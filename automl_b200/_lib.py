@@ -56,6 +56,9 @@ SIGNATURES = {
     'edet_pre_nms': (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
                              ctypes.POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    'edet_pre_nms_topk': (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                  ctypes.POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'edet_nms_work_bytes': (c_size_t, [c_int, c_int]),
     'edet_nms_v5': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                             c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p,

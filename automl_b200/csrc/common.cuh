@@ -119,6 +119,22 @@ __device__ __forceinline__ void apply_act4(float2& a, float2& b) {
   b = apply_act2<ACT>(b);
 }
 
+// Anchor box decode (tf2/anchors.py:30-58), float32, no FMA contraction: `bv` = the four fp16 box
+// logits (ty, tx, th, tw) of one anchor, `an` = its anchor box (ymin, xmin, ymax, xmax).
+__device__ __forceinline__ float4 decode_box(const uint2& bv, const float4& an) {
+  const float2 t01 = __half22float2(*reinterpret_cast<const __half2*>(&bv.x));
+  const float2 t23 = __half22float2(*reinterpret_cast<const __half2*>(&bv.y));
+  const float ty = t01.x, tx = t01.y, th = t23.x, tw = t23.y;
+  const float ycenter_a = __fmul_rn(__fadd_rn(an.x, an.z), 0.5f);
+  const float xcenter_a = __fmul_rn(__fadd_rn(an.y, an.w), 0.5f);
+  const float ha = __fsub_rn(an.z, an.x), wa = __fsub_rn(an.w, an.y);
+  const float w = __fmul_rn(expf(tw), wa), h = __fmul_rn(expf(th), ha);
+  const float yc = __fadd_rn(__fmul_rn(ty, ha), ycenter_a);
+  const float xc = __fadd_rn(__fmul_rn(tx, wa), xcenter_a);
+  const float hh = __fmul_rn(h, 0.5f), hw = __fmul_rn(w, 0.5f);
+  return make_float4(__fsub_rn(yc, hh), __fsub_rn(xc, hw), __fadd_rn(yc, hh), __fadd_rn(xc, hw));
+}
+
 // 8 halves <-> 8 floats through one 128-bit register quad.
 struct alignas(16) Half8 {
   __half2 h[4];

@@ -65,19 +65,8 @@ pre_nms_kernel(const PreParams p, const float* __restrict__ anchors, float* __re
   // box decode (tf2/anchors.py:30-58), float32, no FMA contraction
   const uint2 bv = __ldg(reinterpret_cast<const uint2*>(
       lv.box + (static_cast<size_t>(n) * lv.pixels + pix0 + pl) * p.ld_box + a * 4));
-  const float2 t01 = __half22float2(*reinterpret_cast<const __half2*>(&bv.x));
-  const float2 t23 = __half22float2(*reinterpret_cast<const __half2*>(&bv.y));
-  const float ty = t01.x, tx = t01.y, th = t23.x, tw = t23.y;
-  const float4 an = __ldg(reinterpret_cast<const float4*>(anchors) + anchor);
-  const float ycenter_a = __fmul_rn(__fadd_rn(an.x, an.z), 0.5f);
-  const float xcenter_a = __fmul_rn(__fadd_rn(an.y, an.w), 0.5f);
-  const float ha = __fsub_rn(an.z, an.x), wa = __fsub_rn(an.w, an.y);
-  const float w = __fmul_rn(expf(tw), wa), h = __fmul_rn(expf(th), ha);
-  const float yc = __fadd_rn(__fmul_rn(ty, ha), ycenter_a);
-  const float xc = __fadd_rn(__fmul_rn(tx, wa), xcenter_a);
-  const float hh = __fmul_rn(h, 0.5f), hw = __fmul_rn(w, 0.5f);
   reinterpret_cast<float4*>(boxes)[o] =
-      make_float4(__fsub_rn(yc, hh), __fsub_rn(xc, hw), __fadd_rn(yc, hh), __fadd_rn(xc, hw));
+      decode_box(bv, __ldg(reinterpret_cast<const float4*>(anchors) + anchor));
 }
 
 // ------------------------------------------------------------------------------------------

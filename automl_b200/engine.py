@@ -411,9 +411,13 @@ class Engine(object):
     self.anchors = anchors_lib.Anchors(p.min_level, p.max_level, p.num_scales,
                                        list(p.aspect_ratios), p.anchor_scale, p.image_size)
     anc = self._dev(self.anchors.boxes, f32)
-    K = self.anchors.boxes.shape[0]
-    self.total_anchors = K
+    self.total_anchors = K = self.anchors.boxes.shape[0]
     nms_cfg = p.nms_configs.as_dict() if hasattr(p.nms_configs, 'as_dict') else dict(p.nms_configs)
+    # max_nms_inputs > 0: NMS sees the top-k (anchor, class) pairs instead of one arg-max class
+    # per anchor (tf2/postprocess.py:88-102)
+    self.max_nms_inputs = topk = int(nms_cfg.get('max_nms_inputs', 0) or 0)
+    if topk > 0:
+      K = topk
     iou_t, score_t, tf_sigma = nms_v5_params(nms_cfg)
     self.max_output_size = int(nms_cfg['max_output_size'])
     # Two sets of post-processing buffers: NMS of step i runs on its own stream while the
@@ -436,8 +440,13 @@ class Engine(object):
           'work': self._buf('nms_work%d' % sidx, (ops.nms_work_bytes(n, K),), torch.uint8),
       }
       self._post.append(ps)
-      self._pre_ops.append(lambda ps=ps: ops.pre_nms(cls_l, box_l, level_hw, A, C, anc,
-                                                     ps['boxes'], ps['scores'], ps['classes']))
+      if topk > 0:
+        ps['indices'] = self._buf('indices%d' % sidx, (n, K), torch.int32)
+        self._pre_ops.append(lambda ps=ps: ops.pre_nms_topk(
+            cls_l, box_l, level_hw, A, C, anc, ps['boxes'], ps['scores'], ps['classes'], ps['indices']))
+      else:
+        self._pre_ops.append(lambda ps=ps: ops.pre_nms(cls_l, box_l, level_hw, A, C, anc,
+                                                       ps['boxes'], ps['scores'], ps['classes']))
       self._nms_ops.append(lambda ps=ps: ops.nms_v5(
           ps['boxes'], ps['scores'], ps['classes'], self.image_scales, self.image_id_base,
           self.max_output_size, iou_t, score_t, tf_sigma, (float(H), float(W)),

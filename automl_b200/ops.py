@@ -173,6 +173,21 @@ def pre_nms(cls_levels, box_levels, level_hw, num_anchors, num_classes, anchors,
             _ptr(scores, torch.float32), _ptr(classes, torch.int32), n, _stream())
 
 
+def pre_nms_topk(cls_levels, box_levels, level_hw, num_anchors, num_classes, anchors, boxes, scores,
+                 classes, indices):
+  """Top-k pre-NMS (max_nms_inputs = scores.shape[1]): boxes fp32 [N,k,4], scores fp32 [N,k],
+  classes / indices i32 [N,k]."""
+  levels = len(cls_levels)
+  n, k = scores.shape
+  ld_cls, ld_box = cls_levels[0].shape[-1], box_levels[0].shape[-1]
+  cls_p = (ctypes.c_void_p * levels)(*[_ptr(t, torch.float16).value for t in cls_levels])
+  box_p = (ctypes.c_void_p * levels)(*[_ptr(t, torch.float16).value for t in box_levels])
+  hw = (ctypes.c_int * (2 * levels))(*[v for pair in level_hw for v in pair])
+  _lib.call('edet_pre_nms_topk', cls_p, box_p, hw, levels, ld_cls, ld_box, num_anchors, num_classes,
+            _ptr(anchors, torch.float32), k, _ptr(boxes, torch.float32), _ptr(scores, torch.float32),
+            _ptr(classes, torch.int32), _ptr(indices, torch.int32), n, _stream())
+
+
 def nms_work_bytes(n, k):
   return _lib.load().edet_nms_work_bytes(n, k)
 

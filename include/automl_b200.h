@@ -231,6 +231,21 @@ int edet_nms_v5(const float* boxes, const float* scores, const int32_t* classes,
                 int32_t* valid, void* work, edet_stream_t stream);
 
 /*
+ * Pre-NMS with nms_configs.max_nms_inputs > 0: per image the top max_nms_inputs (anchor, class)
+ * logits (ties: lower flat index anchor*num_classes + class), then sigmoid and box decode of the
+ * selected pairs.  Replaces tf2/postprocess.py:88-102 (topk_class_boxes, top-k branch) inside
+ * pre_nms (:119-156) and tf2/anchors.py:30-58.  Inputs as edet_pre_nms; outputs sorted by
+ * (logit descending, flat index ascending):
+ *   boxes float32 [n, k, 4], scores float32 [n, k], classes int32 [n, k], indices int32 [n, k]
+ *   (anchor index of each row), k = max_nms_inputs <= 8192.
+ */
+int edet_pre_nms_topk(const edet_half* const* h_cls, const edet_half* const* h_box,
+                      const int* h_level_hw /* [levels][2] */, int levels, int ld_cls, int ld_box,
+                      int num_anchors, int num_classes, const float* anchors, int max_nms_inputs,
+                      float* boxes, float* scores, int32_t* classes, int32_t* indices, int n,
+                      edet_stream_t stream);
+
+/*
  * CUDA replacement for nms_np.per_class_nms (nms_np.py:220-264) with the `hard` (nms_np.py:89-126)
  * and `diou` (:28-86) methods: per class greedy NMS in descending score order, float32 "+1 pixel"
  * IoU in nms_np's order of operations (keep decisions bit-identical to NumPy's), survivors of all

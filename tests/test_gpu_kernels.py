@@ -404,6 +404,35 @@ def test_pre_nms(image_size):
   np.testing.assert_allclose(boxes.cpu().numpy(), ref_boxes, rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.parametrize('image_size,topk', [(128, 1000), ((96, 160), 5000), (64, 8192)])
+def test_pre_nms_topk(image_size, topk):
+  """max_nms_inputs > 0 (postprocess.py:88-102): the top-k (anchor, class) pairs.  fp16 logits
+  tie massively at the threshold, so this also checks the lower-flat-index tie rule."""
+  ops = _ops()
+  rng = np.random.default_rng(13)
+  n = 2
+  cls, box = _synthetic_head_outputs(rng, n, image_size)
+  params = _params(image_size, max_nms_inputs=topk)
+  ref_boxes, ref_scores, ref_classes = po.pre_nms(params, cls, box)
+  anc = anchors_lib.Anchors(3, 7, 3, [1.0, 2.0, 0.5], 4.0, image_size).boxes
+  cls_d = [torch.from_numpy(_pad_ld(t, 816)).to(DEV) for t in cls]
+  box_d = [torch.from_numpy(_pad_ld(t, 40)).to(DEV) for t in box]
+  boxes = torch.empty(n, topk, 4, device=DEV)
+  scores = torch.empty(n, topk, device=DEV)
+  classes = torch.empty(n, topk, dtype=torch.int32, device=DEV)
+  indices = torch.empty(n, topk, dtype=torch.int32, device=DEV)
+  hw = [(t.shape[1], t.shape[2]) for t in cls]
+  ops.pre_nms_topk(cls_d, box_d, hw, 9, 90, torch.from_numpy(anc).to(DEV), boxes, scores, classes, indices)
+  torch.cuda.synchronize()
+  np.testing.assert_array_equal(classes.cpu().numpy(), ref_classes)
+  np.testing.assert_allclose(scores.cpu().numpy(), ref_scores, rtol=1e-6, atol=1e-7)
+  np.testing.assert_allclose(boxes.cpu().numpy(), ref_boxes, rtol=1e-5, atol=1e-4)
+  # the anchor index of every row (the oracle's `indices`)
+  flat = np.concatenate([c.reshape(n, -1, 90) for c in cls], axis=1).astype(np.float32).reshape(n, -1)
+  order = np.lexsort((np.arange(flat.shape[1])[None].repeat(n, 0), -flat), axis=-1)[:, :topk]
+  np.testing.assert_array_equal(indices.cpu().numpy(), order // 90)
+
+
 def _nms_inputs(rng, n, k, image=512.0, clustered=True):
   if clustered:
     centres = rng.uniform(0, image, size=(n, 40, 2))

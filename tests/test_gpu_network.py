@@ -96,20 +96,30 @@ def test_network_parity_baseline_configs(name, size, bb_tol, head_tol):
 
 def test_network_parity_lite3():
   """A lite model end to end: relu6, no SE, `sum` fusion, and the fix_head_stem case where the
-  first block is built on the stem's 32 channels although its block args say 40."""
+  first block is built on the stem's 32 channels although its block args say 40.
+  With RANDOM weights this relu6 / un-normalised-sum network is badly conditioned: the oracle's
+  own fp16-STORAGE model (fp32 arithmetic, activations rounded to fp16 between layers) is already
+  1e-3 off at block 5 and 1e-2 off on the box outputs.  The bar is therefore relative to that
+  model: every tensor within 2x the storage-model error + 5e-4."""
   c, a, w, x = _setup('efficientdet-lite3', 128, 1, seed=5)
   assert a.blocks[0].input_filters == 32 and a.blocks[0].mid_filters == 32
   orc = eo.Oracle(c, w, torch.float32)
   cls_ref, box_ref = orc(x)
+  o16 = eo.Oracle(c, w, torch.float32, store=eo.fp16_store)
+  cls_16, box_16 = o16(x)
   eng = _engine(c, w, 1, use_cuda_graph=False)
   cls_out, box_out = eng.forward(torch.from_numpy(x))
   torch.cuda.synchronize()
+  bar = lambda model, ref: 2.0 * rel_l2(model, ref) + 5e-4
   for b in a.blocks:
     got = eng.buffers[b.name + '/out'].float().cpu().permute(0, 3, 1, 2)
-    assert rel_l2(got, orc.endpoints[b.name]) < REL_TOL, b.name
+    assert rel_l2(got, orc.endpoints[b.name]) < bar(o16.endpoints[b.name], orc.endpoints[b.name]), b.name
   for l in a.levels:
-    assert rel_l2(cls_out[l].float().cpu(), cls_ref[l]) < REL_TOL
-    assert rel_l2(box_out[l].float().cpu(), box_ref[l]) < 2.5e-3      # `sum` fusion bar (see below)
+    assert rel_l2(cls_out[l].float().cpu(), cls_ref[l]) < bar(cls_16[l], cls_ref[l]), 'cls %d' % l
+    assert rel_l2(box_out[l].float().cpu(), box_ref[l]) < bar(box_16[l], box_ref[l]), 'box %d' % l
+  for b in a.blocks[:2]:   # the first blocks are still inside the absolute bar
+    got = eng.buffers[b.name + '/out'].float().cpu().permute(0, 3, 1, 2)
+    assert rel_l2(got, orc.endpoints[b.name]) < REL_TOL
 
 
 def test_network_parity_d1_relu6():
@@ -172,6 +182,24 @@ def test_detect_matches_oracle_postprocess_and_graph_replay():
     np.testing.assert_array_equal(det1[i, :, 5], sc)
     np.testing.assert_array_equal(det1[i, :, 1:5], po.clip_boxes(gb[i][idx], 128) * scales[i])
     np.testing.assert_array_equal(det1[i, :, 6], (gc[i][idx] + 1).astype(np.float32))
+
+
+def test_detect_with_topk_pre_nms():
+  """nms_configs.max_nms_inputs > 0: top-k pre-NMS + NMS-V5 end to end against the oracle's
+  post-process of the engine's own head outputs."""
+  c, a, w, x = _setup('efficientdet-d0', 128, 2, seed=4)
+  c.nms_configs.max_nms_inputs = 1000
+  eng = _engine(c, w, 2)
+  det = eng.detect(torch.from_numpy(x)).cpu().numpy()
+  torch.cuda.synchronize()
+  assert eng.scores.shape == (2, 1000)
+  params = c.as_dict()
+  cls_np = [eng.cls_out[l][..., :810].float().cpu().numpy() for l in a.levels]
+  box_np = [eng.box_out[l][..., :36].float().cpu().numpy() for l in a.levels]
+  ref = po.det_post_process(params, cls_np, box_np, np.ones(2, np.float32))
+  np.testing.assert_array_equal(det[..., 6], ref[..., 6])                    # classes
+  np.testing.assert_allclose(det[..., 5], ref[..., 5], rtol=1e-6, atol=1e-7)   # scores
+  np.testing.assert_allclose(det[..., 1:5], ref[..., 1:5], rtol=1e-5, atol=1e-3)
 
 
 def test_efficientdet_call_surface():
