@@ -60,6 +60,7 @@ struct Params {
   const float* bias_d;         // [cmid]
   __half* out;                 // [n, ho, wo, cmid]
   long long* se_sum;           // [n, cmid] or null
+  unsigned* sched;             // dynamic tile scheduler slot (tc_common.cuh)
 };
 
 struct Tile {
@@ -96,6 +97,7 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
   const uint32_t kb_bar = smem_u32(bars + 1);     // MMA k-block retired   (thread 0 only)
   const uint32_t acc_bar = smem_u32(bars + 2);    // accumulator complete  (everyone)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  volatile int* next_tile_s = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -133,7 +135,10 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
   };
 
   bool prefetched = false;   // thread 0 only
-  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+  int t = blockIdx.x;
+  // next_tile_s is double buffered: the slot written in iteration i is rewritten in i + 2, after
+  // every thread has passed the closing barrier of i + 1 (hence its read of iteration i)
+  for (int it = 0; t < p.total_tiles; ++it) {
     const Tile tl = decode(t, p);
     const int cbase = tl.chunk * p.ch;
     const int cv = min(p.ch, p.cmid - cbase);   // valid channels of this chunk (multiple of 8)
@@ -170,7 +175,8 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
     tc_fence_after();
     // the operand buffers are free: fetch the next tile's first k-block under phases 3-4
     if (threadIdx.x == 0) {
-      const int tn = t + gridDim.x;
+      const int tn = sched_next_tile(p.sched, p.total_tiles);
+      next_tile_s[it & 1] = tn;
       prefetched = tn < p.total_tiles;
       if (prefetched) issue_loads(decode(tn, p), 0);
     }
@@ -272,8 +278,9 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
           if (se_s[i] != 0ull) atomicAdd(dst + i, se_s[i]);
       }
     }
-    __syncthreads();   // E tile (and se_s) free for the next tile
+    __syncthreads();   // E tile (and se_s) free for the next tile; next_tile_s published
     tc_fence_after();
+    t = next_tile_s[it & 1];
   }
 
   tc_fence_before();
@@ -354,6 +361,8 @@ extern "C" int edet_mbconv_expand_dw(const edet_half* x, const edet_half* we, co
   p.wd = reinterpret_cast<const __half*>(wd);
   p.out = reinterpret_cast<__half*>(out);
   p.se_sum = reinterpret_cast<long long*>(se_sum);
+  p.sched = next_sched_slot();
+  if (!p.sched) return EDET_ERR_CUDA;
   EDET_CHECK_ARG(smem_bytes <= 232448, "mbconv_expand_dw: tile needs %d bytes of smem", smem_bytes);
   CUtensorMap mx, mw;
   int rc;

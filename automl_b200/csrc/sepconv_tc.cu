@@ -41,6 +41,7 @@ struct Params {
   int n, h, w, c, nout, ldo;
   int katoms, kpad, npad, b_atom_bytes, tmem_cols;
   int tiles_x, tiles_y, total_tiles;
+  unsigned* sched;        // dynamic tile scheduler slot (direct kernel)
 };
 
 template <int ACT_PRE, int ACT_POST>
@@ -302,7 +303,10 @@ sepconv_direct_kernel(const __grid_constant__ CUtensorMap map_w, const Params p)
   uint32_t mma_phase = 0;
   bool weights_ready = false;
 
-  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+  __shared__ int next_tile_s[2];   // double buffered: slot (it & 1) is rewritten two iterations later
+  int t = blockIdx.x;
+  for (int it = 0; t < p.total_tiles; ++it) {
+    if (threadIdx.x == 0) next_tile_s[it & 1] = sched_next_tile(p.sched, p.total_tiles);
     const int tx_i = t % p.tiles_x;
     const int ty_i = (t / p.tiles_x) % p.tiles_y;
     const int n = t / (p.tiles_x * p.tiles_y);
@@ -457,6 +461,7 @@ sepconv_direct_kernel(const __grid_constant__ CUtensorMap map_w, const Params p)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    t = next_tile_s[it & 1];
   }
 
   if (threadIdx.x == 0 && !weights_ready) mbar_wait(w_bar, 0);
@@ -476,9 +481,9 @@ static int launch_direct(const CUtensorMap& mw, const Params& p, int grid, int s
                          cudaStream_t stream) {
   auto kern = sepconv_direct_kernel<POST>;
   static int configured = 0;
-  if (smem_bytes > configured) {
-    EDET_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    configured = 232448;
+  if (smem_bytes > configured) {   // the kernel also has a few bytes of static shared memory
+    EDET_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    configured = 232448 - 1024;
   }
   EDET_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kDirectThreads), smem_bytes, stream, mw, p));
   return EDET_OK;
@@ -537,6 +542,8 @@ extern "C" int edet_sepconv(const edet_fuse_input* h_inputs, int n_inputs, int p
     EDET_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
   cudaStream_t s = as_stream(stream);
+  p.sched = next_sched_slot();
+  if (!p.sched) return EDET_ERR_CUDA;
   const bool direct = n_inputs == 1 && p.fuse.in[0].mode == EDET_RS_SAME &&
                       p.fuse.in[0].weight == 1.0f && pre_act == EDET_ACT_NONE;
   int smem_bytes = 1024 + p.katoms * (kAtomBytesA + p.b_atom_bytes) + 64;

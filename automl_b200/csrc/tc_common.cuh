@@ -136,6 +136,28 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// ---- dynamic tile scheduler for single-role persistent kernels --------------------------------
+// A persistent kernel that walks its tiles with a static stride assumes all its CTAs start
+// together; when another stream (the NMS of the previous batch) holds some SMs, the CTAs that
+// start late still own their full share of tiles and the kernel runs two waves.  Here CTA i owns
+// tile i and every further tile comes from a global counter, so late CTAs simply find less (or
+// no) work.  sched[0] = tiles handed out beyond the first gridDim.x, sched[1] = CTAs that are
+// done; the last CTA resets both, so a slot is reusable by the next launch without a memset.
+__device__ __forceinline__ int sched_next_tile(unsigned* sched, int total_tiles) {
+  const int t = static_cast<int>(gridDim.x + atomicAdd(&sched[0], 1u));
+  if (t >= total_tiles) {     // this CTA's last fetch
+    __threadfence();
+    if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
+      sched[0] = 0u;
+      sched[1] = 0u;
+      __threadfence();
+    }
+  }
+  return t;
+}
+constexpr int kSchedSlots = 256;
+static __device__ unsigned g_tile_sched[2 * kSchedSlots];   // zero-initialised, self-resetting
+
 // ---- host side ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -154,6 +176,20 @@ inline EncodeTiledFn get_encode_fn() {
   }
   fn = reinterpret_cast<EncodeTiledFn>(sym);
   return fn;
+}
+
+// A scheduler slot for one launch (round robin over the pool: launches that may run concurrently
+// -- parallel graph branches -- get distinct slots; the address is baked into the graph node).
+inline unsigned* next_sched_slot() {
+  static unsigned* base = nullptr;
+  static int idx = 0;
+  if (!base && cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_tile_sched) != cudaSuccess) {
+    set_error("cudaGetSymbolAddress(g_tile_sched) failed");
+    return nullptr;
+  }
+  unsigned* s = base + 2 * idx;
+  idx = (idx + 1) % kSchedSlots;
+  return s;
 }
 
 // 3-D half tensor [d2][d1][d0] (d0 contiguous), box [1][box1][64], 128B swizzle.

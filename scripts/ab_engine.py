@@ -30,15 +30,19 @@ for _, e in variants:
   e.set_input(x)
 
 
+POST = os.environ.get('AB_POSTPROCESS', '1') == '1'   # AB_POSTPROCESS=0: network only (no pre-NMS / NMS)
+
+
 def timed(eng, steps=30, warmup=5):
   for _ in range(warmup):
-    eng.run(postprocess=True)
+    eng.run(postprocess=POST)
   torch.cuda.synchronize()
   a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   a.record()
   for _ in range(steps):
-    eng.run(postprocess=True)
-  eng.wait_detections()
+    eng.run(postprocess=POST)
+  if POST:
+    eng.wait_detections()
   b.record()
   torch.cuda.synchronize()
   return a.elapsed_time(b) / steps
