@@ -122,6 +122,15 @@ def cpu_baseline(config, weights, images, seconds_budget=25.0):
                     '+ numpy post-process), %.1f s' % (nimg, IMAGE_SIZE, IMAGE_SIZE, dt)}
 
 
+def workload_config(world):
+  """The `config` object of the JSON line: identical for our arm and the reference arm."""
+  return {'workload': 'EfficientDet-D0 640x640 batch %d/GPU: stem, 16 MBConv, 3 BiFPN cells, '
+                      'class/box heads, pre-NMS, NMS-V5 (gaussian)' % BATCH,
+          'global_batch': world * BATCH, 'parallelism': 'batch-shard x%d' % world,
+          'l2': 'inputs (157 MB fp32) and per-step activations (GBs) exceed the 126 MB L2, '
+                'so every timed iteration starts with a flushed L2'}
+
+
 def run_reference(args, rank, world):
   """--impl reference: the reference's CPU implementation of the path (oracle port)."""
   if rank != 0:
@@ -145,8 +154,9 @@ def run_reference(args, rank, world):
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * BATCH / v,
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
       'data': 'synthetic',
-      'config': {'workload': 'EfficientDet-D0 640x640 batch %d forward+postprocess' % BATCH,
-                 'note': 'TensorFlow is not installable offline; oracle port of the reference path'},
+      'config': dict(workload_config(world),
+                     note='TensorFlow is not installable offline: the oracle port of the reference '
+                          'path on the host cores, a bounded sample of the batch per step'),
       'cpu_baseline': base,
       'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
   }
@@ -291,11 +301,7 @@ def main():
         'steps': args.steps, 'warmup': max(3, args.warmup),
         'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f16 storage / f32 accumulate', 'data': 'synthetic',
-        'config': {'workload': 'EfficientDet-D0 640x640 batch %d/GPU: stem, 16 MBConv, 3 BiFPN cells, '
-                               'class/box heads, pre-NMS, NMS-V5 (gaussian)' % BATCH,
-                   'global_batch': world * BATCH, 'parallelism': 'batch-shard x%d' % world,
-                   'l2': 'inputs (157 MB fp32) and per-step activations (GBs) exceed the 126 MB L2, '
-                         'so every timed iteration starts with a flushed L2'},
+        'config': workload_config(world),
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
                 'h2d_bytes_per_step': int(host_raw.numel()) + 4 * BATCH,
                 'd2h_bytes_per_step': int(world * BATCH * eng.max_output_size * 7 * 4),
