@@ -38,3 +38,36 @@ def test_no_product_import_of_oracle():
         with open(os.path.join(dirpath, fn)) as f:
           src = f.read()
         assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), fn
+
+
+def _declared_prototypes():
+  """name -> list of parameter declarations, parsed from the header (comments stripped)."""
+  with open(os.path.join(ROOT, 'include', 'automl_b200.h')) as f:
+    text = f.read()
+  text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+  protos = {}
+  for m in re.finditer(r'\b(edet_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S):
+    params = [p.strip() for p in m.group(2).replace('\n', ' ').split(',')]
+    if params in ([''], ['void']):
+      params = []
+    protos[m.group(1)] = params
+  return protos
+
+
+def test_ctypes_signatures_match_header_prototypes():
+  """The ctypes binding (what a reference maintainer would vendor) has, for every
+  entry point, as many arguments as the header prototype, pointers where the header has pointers
+  or the stream handle, and c_int / c_float where it has scalars."""
+  protos = _declared_prototypes()
+  assert sorted(protos) == sorted(_lib.SIGNATURES)
+  for name, params in protos.items():
+    _, argtypes = _lib.SIGNATURES[name]
+    assert len(argtypes) == len(params), (name, len(argtypes), params)
+    for decl, ct in zip(params, argtypes):
+      is_ptr = '*' in decl or decl.startswith('edet_stream_t')
+      if is_ptr:
+        assert ct is ctypes.c_void_p or hasattr(ct, 'contents') or ct is ctypes.c_char_p, (name, decl, ct)
+      elif decl.startswith('float'):
+        assert ct is ctypes.c_float, (name, decl, ct)
+      elif decl.startswith('int'):
+        assert ct is ctypes.c_int, (name, decl, ct)
