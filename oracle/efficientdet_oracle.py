@@ -23,9 +23,11 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from automl_b200 import fpn_configs
-from automl_b200 import utils as host_utils
-from automl_b200.backbone import efficientnet_builder
+from oracle import structure_oracle
+
+# Inference BatchNorm epsilon of the EfficientNet backbones and of the detector's own layers
+# (backbone/efficientnet_builder.py:191, efficientnet_lite_builder.py:69; utils.py:244-257).
+BN_EPSILON = 1e-3
 
 
 # ------------------------------------------------------------------------------------
@@ -127,8 +129,9 @@ class Oracle(object):
   def backbone(self, x):
     p = self.p
     name = p.backbone_name
-    gp, _, blocks = efficientnet_builder.backbone_spec(name, {'act_type': p.act_type})
-    eps = gp.batch_norm_epsilon
+    # the oracle's own walk of the block strings (oracle/structure_oracle.py), NOT the product's
+    _, blocks = structure_oracle.backbone_blocks(name)
+    eps = BN_EPSILON
     act = lambda t: activation_fn(t, p.act_type)
     w = self.w
     # Stem :526-527
@@ -137,27 +140,27 @@ class Oracle(object):
     self.endpoints['stem'] = x
     feats = {}
     for b in blocks:
-      scope = '%s/%s' % (name, b.name)
+      scope = '%s/%s' % (name, b['name'])
       inputs = x
-      if b.expand_name:
-        x = conv2d_same(x, w['%s/%s/kernel' % (scope, b.expand_name)])
-        x = self.store(act(batch_norm_inference(x, w, '%s/%s' % (scope, b.expand_bn), eps)))
-      x = depthwise_conv2d_same(x, w[scope + '/depthwise_conv2d/depthwise_kernel'], b.stride)
-      x = self.store(act(batch_norm_inference(x, w, '%s/%s' % (scope, b.dw_bn), eps)))
-      if b.se_filters:
+      if b['expand_conv']:
+        x = conv2d_same(x, w['%s/%s/kernel' % (scope, b['expand_conv'])])
+        x = self.store(act(batch_norm_inference(x, w, '%s/%s' % (scope, b['expand_bn']), eps)))
+      x = depthwise_conv2d_same(x, w[scope + '/depthwise_conv2d/depthwise_kernel'], b['stride'])
+      x = self.store(act(batch_norm_inference(x, w, '%s/%s' % (scope, b['dw_bn']), eps)))
+      if b['has_se']:
         se = x.mean(dim=(2, 3), keepdim=True)
         se = conv2d_same(se, w[scope + '/se/conv2d/kernel']) + w[scope + '/se/conv2d/bias'].view(1, -1, 1, 1)
         se = act(se)
         se = conv2d_same(se, w[scope + '/se/conv2d_1/kernel']) + w[scope + '/se/conv2d_1/bias'].view(1, -1, 1, 1)
         x = torch.sigmoid(se) * x
-      x = conv2d_same(x, w['%s/%s/kernel' % (scope, b.project_name)])
-      x = batch_norm_inference(x, w, '%s/%s' % (scope, b.project_bn), eps)
-      if b.has_skip:
+      x = conv2d_same(x, w['%s/%s/kernel' % (scope, b['project_conv'])])
+      x = batch_norm_inference(x, w, '%s/%s' % (scope, b['project_bn']), eps)
+      if b['has_skip']:
         x = x + inputs
       x = self.store(x)
-      self.endpoints[b.name] = x
-      if b.reduction:
-        feats[b.reduction] = x
+      self.endpoints[b['name']] = x
+      if b['reduction']:
+        feats[b['reduction']] = x
     return feats, eps
 
   # -- efficientdet_arch.py:55-132 --------------------------------------------------------
@@ -200,19 +203,24 @@ class Oracle(object):
   def build_bifpn_layer(self, feats, feat_sizes, rep, eps):
     p = self.p
     w = self.w
-    fpn_config = p.fpn_config or fpn_configs.get_fpn_config(
-        p.fpn_name, p.min_level, p.max_level, p.fpn_weight_method)
+    if p.fpn_config:
+      weight_method = p.fpn_config.weight_method
+      nodes_cfg = [dict(n) if isinstance(n, dict) else n.as_dict() for n in p.fpn_config.nodes]
+    else:
+      if (p.fpn_name or 'bifpn') not in ('bifpn', 'bifpn_dyn'):
+        raise NotImplementedError('fpn_name %r' % p.fpn_name)
+      weight_method = p.fpn_weight_method or 'fastattn'    # tf2/fpn_configs.py:27
+      nodes_cfg = [{'feat_level': lvl, 'inputs_offsets': offs}
+                   for lvl, offs in structure_oracle.bifpn_nodes(p.min_level, p.max_level)]
     feats = list(feats)
-    nodes_cfg = [dict(n) if isinstance(n, dict) else n.as_dict() for n in fpn_config.nodes]
     for i, fnode in enumerate(nodes_cfg):
       scope = 'fpn_cells/cell_%d/fnode%d' % (rep, i)
-      th = feat_sizes[fnode['feat_level']]['height']
-      tw = feat_sizes[fnode['feat_level']]['width']
+      th, tw = feat_sizes[fnode['feat_level']]
       nodes = []
       for idx, off in enumerate(fnode['inputs_offsets']):
         nodes.append(self.resample_feature_map(
             feats[off], '%s/resample_%d_%d_%d' % (scope, idx, off, len(feats)), th, tw, eps))
-      new_node = self.fuse_features(nodes, fpn_config.weight_method, scope)
+      new_node = self.fuse_features(nodes, weight_method, scope)
       op = '%s/op_after_combine%d' % (scope, len(feats))
       new_node = activation_fn(new_node, p.act_type)
       new_node = depthwise_conv2d_same(new_node, w[op + '/conv/depthwise_kernel'])
@@ -231,7 +239,7 @@ class Oracle(object):
   # -- efficientdet_arch.py:352-415 -------------------------------------------------------
   def build_feature_network(self, features, eps):
     p = self.p
-    feat_sizes = host_utils.get_feat_sizes(p.image_size, p.max_level)
+    feat_sizes = structure_oracle.feature_sizes(p.image_size, p.max_level)
     feats = []
     if p.min_level not in features:
       raise ValueError('features.keys ({}) should include min_level ({})'.format(
@@ -243,8 +251,11 @@ class Oracle(object):
         h, wd = feats[-1].shape[2], feats[-1].shape[3]
         feats.append(self.store(self.resample_feature_map(
             feats[-1], 'resample_p%d' % level, (h - 1) // 2 + 1, (wd - 1) // 2 + 1, eps)))
-    host_utils.verify_feats_size([(f.shape[2], f.shape[3]) for f in feats], feat_sizes,
-                                 p.min_level, p.max_level)
+    # utils.verify_feats_size (utils.py:552-573)
+    for f, size in zip(feats, feat_sizes[p.min_level:p.max_level + 1]):
+      if (f.shape[2], f.shape[3]) != tuple(size):
+        raise ValueError('feats has shape {} but it should be {}'.format(
+            (f.shape[2], f.shape[3]), size))
     new_feats = None
     for rep in range(p.fpn_cell_repeats):
       new_feats = self.build_bifpn_layer(feats, feat_sizes, rep, eps)
