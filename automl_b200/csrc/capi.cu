@@ -2,7 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
-#include "common.cuh"
+#include <atomic>
+
+#include "tc_common.cuh"
 
 namespace edet {
 static thread_local char g_err[512] = "";
@@ -12,6 +14,54 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+    set_error("cudaGetDevice failed or device ordinal %d >= %d", dev, kMaxDevices);
+    return -1;
+  }
+  return dev;
+}
+
+int device_sm_count() {
+  static std::atomic<int> cached[kMaxDevices];
+  const int dev = current_device();
+  if (dev < 0) return 0;
+  int v = cached[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+      set_error("cudaDeviceGetAttribute(MultiProcessorCount) failed");
+      return 0;
+    }
+    cached[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+namespace pwtc {
+// zero-initialised in every context that loads the module; each slot resets itself
+__device__ unsigned g_tile_sched[2 * kSchedSlots];
+
+unsigned* next_sched_slot() {
+  static std::atomic<unsigned*> base[kMaxDevices];
+  static std::atomic<unsigned> next[kMaxDevices];
+  const int dev = current_device();
+  if (dev < 0) return nullptr;
+  unsigned* b = base[dev].load(std::memory_order_acquire);
+  if (b == nullptr) {
+    void* addr = nullptr;
+    if (cudaGetSymbolAddress(&addr, g_tile_sched) != cudaSuccess || addr == nullptr) {
+      set_error("cudaGetSymbolAddress(g_tile_sched) failed");
+      return nullptr;
+    }
+    b = static_cast<unsigned*>(addr);
+    base[dev].store(b, std::memory_order_release);
+  }
+  const unsigned i = next[dev].fetch_add(1u, std::memory_order_relaxed) % kSchedSlots;
+  return b + 2 * i;
+}
+}  // namespace pwtc
 }  // namespace edet
 
 extern "C" int edet_version(void) { return 100; }

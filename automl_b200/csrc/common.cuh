@@ -166,6 +166,27 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 
 inline cudaStream_t as_stream(edet_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- per-device state (capi.cu) -------------------------------------------------------------
+// Everything the launch wrappers cache about "the device" is keyed by the CURRENT device ordinal:
+// one process may drive several engines on several GPUs (Engine(device=...)), so a process-wide
+// static would hand cuda:1 the SM count, scheduler-counter address and shared-memory opt-in
+// state of cuda:0.
+constexpr int kMaxDevices = 64;
+int current_device();                 // ordinal of the current device, -1 (+ error text) on failure
+int device_sm_count();                // multiprocessor count of the current device, 0 on failure
+// Opt a kernel into `bytes` of dynamic shared memory once per (kernel instantiation, device).
+// `done` is the caller's zero-initialised static int[kMaxDevices] (one per instantiation), so no
+// CUDA API call is made on the steady-state / graph-capture path.
+template <typename F>
+inline int ensure_dynamic_smem(F kernel, int bytes, int* done) {
+  const int dev = current_device();
+  if (dev < 0) return EDET_ERR_CUDA;
+  if (done[dev] >= bytes) return EDET_OK;
+  EDET_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[dev] = bytes;
+  return EDET_OK;
+}
+
 // Programmatic dependent launch (PDL): every kernel of the path is launched with the
 // programmatic-stream-serialization attribute, signals `launch_dependents` as its first
 // instruction and executes `griddepcontrol.wait` before it touches global memory.  The NEXT

@@ -332,12 +332,8 @@ static int pick_block_n(int nout) {
 template <int ACT, bool HAS_RES>
 static int launch(const Maps& maps, const Params& p, int grid, int smem_bytes, cudaStream_t stream) {
   auto kern = conv_tc_kernel<ACT, HAS_RES>;
-  static int configured_smem = 0;
-  if (smem_bytes > configured_smem) {
-    EDET_CHECK_CUDA(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    configured_smem = kSmemLimit;
-  }
+  static int configured[kMaxDevices];
+  if (int rc = ensure_dynamic_smem(kern, kSmemLimit, configured)) return rc;
   EDET_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem_bytes, stream, maps, p));
   return EDET_OK;
 }
@@ -413,12 +409,8 @@ extern "C" int edet_conv2d(const edet_half* in, const edet_half* wt, const float
     return rc;
   if ((rc = make_map4(&maps.o, out, cout, p.wo, p.ho, n, 64, TW, 2))) return rc;
 
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    EDET_CHECK_CUDA(cudaGetDevice(&dev));
-    EDET_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sm_count = device_sm_count();
+  if (!sm_count) return EDET_ERR_CUDA;
   const int grid = p.total_tiles < 2 * sm_count ? p.total_tiles : 2 * sm_count;
   const bool has_res = residual != nullptr;
   cudaStream_t s = as_stream(stream);

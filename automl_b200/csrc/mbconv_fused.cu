@@ -300,12 +300,8 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p,
 #define EDET_MBF(ACT, SE)                                                                     \
   do {                                                                                        \
     auto kern = mbconv_front_kernel<K, S, ACT, SE>;                                           \
-    static int configured = 0;                                                                \
-    if (smem_bytes > configured) {                                                            \
-      EDET_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           232448));                                          \
-      configured = 232448;                                                                    \
-    }                                                                                         \
+    static int configured[kMaxDevices];                                                       \
+    if (int rc = ensure_dynamic_smem(kern, 232448, configured)) return rc;                    \
     EDET_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem_bytes, stream, mx, mw, p)); \
     return EDET_OK;                                                                           \
   } while (0)
@@ -369,12 +365,8 @@ extern "C" int edet_mbconv_expand_dw(const edet_half* x, const edet_half* we, co
   if ((rc = make_map4(&mx, x, cin, w, h, n, p.block_k, kPatch, kPatch))) return rc;
   if ((rc = make_map(&mw, we, cin, cmid, 1, cin, static_cast<uint64_t>(cmid) * cin, p.ch, p.block_k)))
     return rc;
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    EDET_CHECK_CUDA(cudaGetDevice(&dev));
-    EDET_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sm_count = device_sm_count();
+  if (!sm_count) return EDET_ERR_CUDA;
   // CTAs per SM the resources allow (smem and TMEM columns)
   int per_sm = 232448 / (smem_bytes + 1024);
   if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;

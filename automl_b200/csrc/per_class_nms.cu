@@ -428,16 +428,9 @@ extern "C" int edet_per_class_nms(const float* boxes, const float* scores, const
     set_error("per_class_nms: unknown method %d", method);
     return EDET_ERR_INVALID;
   }
-  static bool configured = false;
-  if (!configured) {
-    EDET_CHECK_CUDA(cudaFuncSetAttribute(per_class_nms_kernel<false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(Smem))));
-    EDET_CHECK_CUDA(cudaFuncSetAttribute(per_class_nms_kernel<true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(Smem))));
-    configured = true;
-  }
+  static int configured[2][kMaxDevices];
+  if (int rc = ensure_dynamic_smem(per_class_nms_kernel<false>, static_cast<int>(sizeof(Smem)), configured[0])) return rc;
+  if (int rc = ensure_dynamic_smem(per_class_nms_kernel<true>, static_cast<int>(sizeof(Smem)), configured[1])) return rc;
   if (method == EDET_NMS_DIOU)
     per_class_nms_kernel<true><<<n, kThreads, sizeof(Smem), s>>>(
         boxes, scores, classes, image_ids, image_scales, k, num_classes, max_boxes_to_draw,

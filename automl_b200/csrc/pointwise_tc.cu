@@ -313,12 +313,8 @@ template <int ACT, bool HAS_RES>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo,
                   const Params& p, int grid, int smem_bytes, cudaStream_t stream) {
   auto kern = pointwise_tc_kernel<ACT, HAS_RES>;
-  static int configured_smem = 0;  // per instantiation; avoids API calls inside graph capture
-  if (smem_bytes > configured_smem) {
-    EDET_CHECK_CUDA(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    configured_smem = kSmemLimit;
-  }
+  static int configured[kMaxDevices];   // per instantiation and device; no API call once set
+  if (int rc = ensure_dynamic_smem(kern, kSmemLimit, configured)) return rc;
   EDET_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem_bytes, stream, ma, mw, mo, p));
   return EDET_OK;
 }
@@ -377,12 +373,8 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   if ((rc = make_map(&mo, out, nout, rows, batch, ldo, static_cast<uint64_t>(rows) * ldo, 32)))
     return rc;
 
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    EDET_CHECK_CUDA(cudaGetDevice(&dev));
-    EDET_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sm_count = device_sm_count();
+  if (!sm_count) return EDET_ERR_CUDA;
   const int grid = p.total_tiles < 2 * sm_count ? p.total_tiles : 2 * sm_count;
   const bool has_res = residual != nullptr;
 

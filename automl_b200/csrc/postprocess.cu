@@ -765,13 +765,8 @@ extern "C" int edet_nms_v5(const float* boxes, const float* scores, const int32_
   float* ws = reinterpret_cast<float*>(work);
   int32_t* wb = reinterpret_cast<int32_t*>(ws + static_cast<size_t>(n) * k);
   int32_t* need_full = wb + static_cast<size_t>(n) * k;
-  static bool configured = false;
-  if (!configured) {
-    EDET_CHECK_CUDA(cudaFuncSetAttribute(nms_v5_fast_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(BatchSmem))));
-    configured = true;
-  }
+  static int configured[kMaxDevices];
+  if (int rc = ensure_dynamic_smem(nms_v5_fast_kernel, static_cast<int>(sizeof(BatchSmem)), configured)) return rc;
   // fast path (top candidates in shared memory, exactness proven per image) ...
   nms_v5_fast_kernel<<<n, kBT, sizeof(BatchSmem), as_stream(stream)>>>(
       boxes, scores, classes, image_scales, image_id_base, k, max_output_size, iou_threshold,

@@ -241,12 +241,8 @@ extern "C" int edet_pre_nms_topk(const edet_half* const* h_cls, const edet_half*
                  "pre_nms_topk: max_nms_inputs must be in 1..min(%d, anchors*classes) (got %d)", kMaxK,
                  max_nms_inputs);
   EDET_CHECK_ARG(total < 0xffffffffLL, "pre_nms_topk: too many (anchor, class) pairs");
-  static bool configured = false;
-  if (!configured) {
-    EDET_CHECK_CUDA(cudaFuncSetAttribute(pre_nms_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(Smem))));
-    configured = true;
-  }
+  static int configured[kMaxDevices];
+  if (int rc = ensure_dynamic_smem(pre_nms_topk_kernel, static_cast<int>(sizeof(Smem)), configured)) return rc;
   pre_nms_topk_kernel<<<n, kThreads, sizeof(Smem), as_stream(stream)>>>(p, anchors, boxes, scores,
                                                                        classes, indices);
   EDET_CHECK_LAUNCH();

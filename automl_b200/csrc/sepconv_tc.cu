@@ -480,11 +480,8 @@ template <int POST>
 static int launch_direct(const CUtensorMap& mw, const Params& p, int grid, int smem_bytes,
                          cudaStream_t stream) {
   auto kern = sepconv_direct_kernel<POST>;
-  static int configured = 0;
-  if (smem_bytes > configured) {   // the kernel also has a few bytes of static shared memory
-    EDET_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-    configured = 232448 - 1024;
-  }
+  static int configured[kMaxDevices];   // the kernel also has a few bytes of static shared memory
+  if (int rc = ensure_dynamic_smem(kern, 232448 - 1024, configured)) return rc;
   EDET_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kDirectThreads), smem_bytes, stream, mw, p));
   return EDET_OK;
 }
@@ -493,11 +490,8 @@ template <int PRE, int POST>
 static int launch(const CUtensorMap& mw, const Params& p, int grid, int smem_bytes,
                   cudaStream_t stream) {
   auto kern = sepconv_kernel<PRE, POST>;
-  static int configured = 0;
-  if (smem_bytes > configured) {
-    EDET_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    configured = 232448;
-  }
+  static int configured[kMaxDevices];
+  if (int rc = ensure_dynamic_smem(kern, 232448, configured)) return rc;
   EDET_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem_bytes, stream, mw, p));
   return EDET_OK;
 }
@@ -535,12 +529,8 @@ extern "C" int edet_sepconv(const edet_fuse_input* h_inputs, int n_inputs, int p
   CUtensorMap mw;
   if (int rc = make_map(&mw, pw_wt, c, nout, 1, c, static_cast<uint64_t>(nout) * c, p.npad, 64))
     return rc;
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    EDET_CHECK_CUDA(cudaGetDevice(&dev));
-    EDET_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sm_count = device_sm_count();
+  if (!sm_count) return EDET_ERR_CUDA;
   cudaStream_t s = as_stream(stream);
   p.sched = next_sched_slot();
   if (!p.sched) return EDET_ERR_CUDA;

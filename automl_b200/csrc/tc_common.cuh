@@ -155,9 +155,8 @@ __device__ __forceinline__ int sched_next_tile(unsigned* sched, int total_tiles)
   }
   return t;
 }
-constexpr int kSchedSlots = 256;
-static __device__ unsigned g_tile_sched[2 * kSchedSlots];   // zero-initialised, self-resetting
-
+// Pool of self-resetting scheduler counters, one pool per device (defined in capi.cu).
+constexpr int kSchedSlots = 4096;
 // ---- host side ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -178,19 +177,12 @@ inline EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// A scheduler slot for one launch (round robin over the pool: launches that may run concurrently
-// -- parallel graph branches -- get distinct slots; the address is baked into the graph node).
-inline unsigned* next_sched_slot() {
-  static unsigned* base = nullptr;
-  static int idx = 0;
-  if (!base && cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_tile_sched) != cudaSuccess) {
-    set_error("cudaGetSymbolAddress(g_tile_sched) failed");
-    return nullptr;
-  }
-  unsigned* s = base + 2 * idx;
-  idx = (idx + 1) % kSchedSlots;
-  return s;
-}
+// A scheduler slot ({next tile, finished CTAs} counter pair) for one launch, from the CURRENT
+// device's pool, handed out round robin with an atomic index: launches that may run concurrently
+// (parallel graph branches, several engines) get distinct slots as long as fewer than kSchedSlots
+// launches are alive at once; the address is baked into the graph node.  nullptr (+ error text)
+// on failure.  Defined in capi.cu.
+unsigned* next_sched_slot();
 
 // 3-D half tensor [d2][d1][d0] (d0 contiguous), box [1][box1][64], 128B swizzle.
 inline int make_map(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,

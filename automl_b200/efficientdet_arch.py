@@ -11,8 +11,10 @@ Differences forced by the runtime: `features` is a float32 CUDA tensor (or anyth
 torch.as_tensor accepts; it is copied to the device), and variables are not created inside a
 TF graph: pass them with `weights=` (dict keyed by reference variable names, Keras layouts).
 Without `weights`, seeded synthetic weights are used, like `ckpt_path='_'` in the reference.
-Engines are cached per (config, batch, weights identity).
+Engines are cached per (config, batch, weights object, device) in a small LRU that keeps the
+weights object alive (clear_engines() empties it).
 """
+import collections
 import json
 
 import torch
@@ -22,7 +24,17 @@ from automl_b200 import weights as weights_lib
 from automl_b200.arch import DetArch
 from automl_b200.engine import Engine
 
-_ENGINE_CACHE = {}
+# key -> (engine, weights object).  The entry keeps the weights dict alive, so `id(weights)` in
+# the key cannot be recycled by CPython for a different checkpoint while the entry exists; the
+# cache is a small LRU so engines (device buffers + CUDA graphs) of configurations that are no
+# longer used are released.
+_ENGINE_CACHE = collections.OrderedDict()
+ENGINE_CACHE_SIZE = 4
+
+
+def clear_engines():
+  """Drops every cached engine (their device buffers and graphs are freed with them)."""
+  _ENGINE_CACHE.clear()
 
 
 def resolve_config(model_name=None, config=None, **kwargs):
@@ -38,14 +50,21 @@ def resolve_config(model_name=None, config=None, **kwargs):
 
 
 def get_engine(config, batch_size, weights=None, device='cuda:0', **engine_kwargs):
+  """Engine for (config, batch, weights OBJECT, device).  The weights dict is treated as
+  immutable once passed: edit a copy (a new dict is a new cache key), or call clear_engines()."""
   key = (json.dumps(config.as_dict(), sort_keys=True, default=str), int(batch_size),
-         id(weights), str(device), tuple(sorted(engine_kwargs.items())))
-  eng = _ENGINE_CACHE.get(key)
-  if eng is None:
-    if weights is None:
-      weights = weights_lib.synthetic_weights(DetArch(config), seed=0)
-    eng = Engine(config, weights, batch_size, device=device, **engine_kwargs)
-    _ENGINE_CACHE[key] = eng
+         id(weights) if weights is not None else None, str(device),
+         tuple(sorted(engine_kwargs.items())))
+  hit = _ENGINE_CACHE.get(key)
+  if hit is not None and hit[1] is weights:
+    _ENGINE_CACHE.move_to_end(key)
+    return hit[0]
+  w = weights if weights is not None else weights_lib.synthetic_weights(DetArch(config), seed=0)
+  eng = Engine(config, w, batch_size, device=device, **engine_kwargs)
+  _ENGINE_CACHE[key] = (eng, weights)
+  _ENGINE_CACHE.move_to_end(key)
+  while len(_ENGINE_CACHE) > ENGINE_CACHE_SIZE:
+    _ENGINE_CACHE.popitem(last=False)
   return eng
 
 

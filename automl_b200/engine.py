@@ -422,8 +422,6 @@ class Engine(object):
     self.max_output_size = int(nms_cfg['max_output_size'])
     # Two sets of post-processing buffers: NMS of step i runs on its own stream while the
     # network of step i+1 (which writes the OTHER set) already runs on the main stream.
-    self.image_scales = self._buf('image_scales', (n,), f32)
-    self.image_scales.fill_(1.0)
     self._post = []
     cls_l = [self.cls_out[l] for l in a.levels]
     box_l = [self.box_out[l] for l in a.levels]
@@ -438,7 +436,11 @@ class Engine(object):
           'sel_index': self._buf('sel_index%d' % sidx, (n, self.max_output_size), torch.int32),
           'valid': self._buf('valid%d' % sidx, (n,), torch.int32),
           'work': self._buf('nms_work%d' % sidx, (ops.nms_work_bytes(n, K),), torch.uint8),
+          # per set: the NMS of step i (own stream) may still read its scales while the caller
+          # already stages the scales of step i+1
+          'image_scales': self._buf('image_scales%d' % sidx, (n,), f32),
       }
+      ps['image_scales'].fill_(1.0)
       self._post.append(ps)
       if topk > 0:
         ps['indices'] = self._buf('indices%d' % sidx, (n, K), torch.int32)
@@ -448,7 +450,7 @@ class Engine(object):
         self._pre_ops.append(lambda ps=ps: ops.pre_nms(cls_l, box_l, level_hw, A, C, anc,
                                                        ps['boxes'], ps['scores'], ps['classes']))
       self._nms_ops.append(lambda ps=ps: ops.nms_v5(
-          ps['boxes'], ps['scores'], ps['classes'], self.image_scales, self.image_id_base,
+          ps['boxes'], ps['scores'], ps['classes'], ps['image_scales'], self.image_id_base,
           self.max_output_size, iou_t, score_t, tf_sigma, (float(H), float(W)),
           ps['detections'], ps['sel_index'], ps['valid'], ps['work']))
     self._cur = 0
@@ -491,6 +493,13 @@ class Engine(object):
         fn()
     for st in open_branches.values():
       main.wait_stream(st)
+
+  @property
+  def image_scales(self):
+    """float32 [N] image_scale_to_original of the NEXT run(postprocess=True): write it (on the
+    current stream) before calling run() / detect().  One buffer per post-processing set, so
+    staging step i+1 never races the NMS of step i."""
+    return self._post[self._step % 2]['image_scales']
 
   # buffers of the most recent post-processed step
   @property

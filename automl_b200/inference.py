@@ -69,6 +69,30 @@ def _rgb3(v):
   return [float(x) for x in v]
 
 
+class _Request(object):
+  """Handle of one in-flight serving request (ServingDriver.submit)."""
+
+  def __init__(self, slot):
+    self._slot = slot
+    self._out = None
+
+  def _finish(self):
+    if self._out is None:
+      self._slot['ev_done'].synchronize()
+      self._out = self._slot['host_det'].numpy().copy()
+      if self._slot['pending'] is self:
+        self._slot['pending'] = None
+    return self._out
+
+  def done(self):
+    return self._out is not None or self._slot['ev_done'].query()
+
+  def result(self):
+    """float32 [N (x world), max_output_size, 7] numpy array
+    [image_id, ymin, xmin, ymax, xmax, score, class]."""
+    return self._finish()
+
+
 class ServingDriver(object):
   """A driver for serving single or batch images (reference inference.py:340)."""
 
@@ -91,62 +115,130 @@ class ServingDriver(object):
     self.line_thickness = line_thickness
     self.device = device
     self.image_id_base = image_id_base
-    self._raw_shape = None
+    self._engines = None
 
   # ---- build ---------------------------------------------------------------------------------
   def build(self, params_override=None):
-    """Builds the engine (weights, buffers, launch list) and returns the signature dict."""
+    """Builds the engine (weights, buffers, launch list) and returns the signature dict.
+
+    batch_size=None (the reference's dynamic batch, inference.py:68-109, where `map_fn` runs the
+    per-image pre-process over however many images arrive): the weights are loaded here and one
+    engine per distinct batch size is built on first use and kept."""
     params = copy.deepcopy(self.params)
     if params_override:
       params.update(params_override)
-    if not self.batch_size:
-      raise NotImplementedError('dynamic batch size: pass the serving batch_size explicitly')
     config = hparams_config.Config(params)
     arch = DetArch(config)
-    weights = load_weights(self.ckpt_path, arch)
+    self._weights = load_weights(self.ckpt_path, arch)
     self.config = config
-    self.engine = Engine(config, weights, self.batch_size, device=self.device,
-                         image_id_base=self.image_id_base)
     self.mean_rgb = _rgb3(params['mean_rgb'])
     self.stddev_rgb = _rgb3(params['stddev_rgb'])
-    self._host_det = torch.empty(self.batch_size, self.engine.max_output_size, 7).pin_memory()
-    self._scales = torch.empty(self.batch_size, dtype=torch.float32).pin_memory()
-    self._gathered = None
-    if torch.distributed.is_available() and torch.distributed.is_initialized():
-      world = torch.distributed.get_world_size()
-      if world > 1:
-        self._gathered = torch.empty(world * self.batch_size, self.engine.max_output_size, 7,
-                                     device=self.device)
+    self._engines = {}
+    self._slots = {}
+    self._copy_stream = torch.cuda.Stream(device=self.device)
+    self._seq = 0
+    self.engine = self._engine_for(self.batch_size) if self.batch_size else None
     self.signitures = {
         'image_files': 'image_files',     # bytes of encoded images (serve_files)
         'image_arrays': 'image_arrays',   # uint8 HxWx3 arrays (serve_images)
-        'prediction': self.engine.detections,
+        'prediction': self.engine.detections if self.engine is not None else 'detections',
     }
     return self.signitures
 
+  def _engine_for(self, n):
+    eng = self._engines.get(n)
+    if eng is None:
+      eng = self._engines[n] = Engine(self.config, self._weights, n, device=self.device,
+                                      image_id_base=self.image_id_base)
+      world = 1
+      if torch.distributed.is_available() and torch.distributed.is_initialized():
+        world = torch.distributed.get_world_size()
+      # two in-flight requests per batch size: pinned host staging / result buffers, device raw
+      # buffers and the events that order their reuse
+      self._slots[n] = [{
+          'host_det': torch.empty(world * n, eng.max_output_size, 7).pin_memory(),
+          'scales': torch.empty(n, dtype=torch.float32).pin_memory(),
+          'gathered': (torch.empty(world * n, eng.max_output_size, 7, device=self.device)
+                       if world > 1 else None),
+          'raw_host': None, 'raw_dev': None,
+          'ev_h2d': torch.cuda.Event(), 'ev_raw_free': torch.cuda.Event(),
+          'ev_done': torch.cuda.Event(), 'pending': None,
+      } for _ in range(2)]
+    return eng
+
   # ---- serving -------------------------------------------------------------------------------
-  def _stage_raw(self, image_arrays):
-    """Uploads the uint8 images and runs the device pre-process into the engine input."""
-    eng = self.engine
-    if len(image_arrays) != self.batch_size:
-      raise ValueError('expected %d images, got %d' % (self.batch_size, len(image_arrays)))
+  def _stage_raw(self, eng, slot, image_arrays):
+    """Uploads the uint8 images (copy stream, from pinned memory) and runs the device pre-process
+    into the engine input (current stream)."""
+    n = eng.n
+    main = torch.cuda.current_stream()
     if isinstance(image_arrays, torch.Tensor):   # [N,h,w,3] uint8 (e.g. pinned host memory)
       shapes = {tuple(image_arrays.shape[1:])}
     else:
       shapes = {tuple(np.shape(im)) for im in image_arrays}
     if len(shapes) == 1:
-      if isinstance(image_arrays, torch.Tensor):
+      shape = (n,) + next(iter(shapes))
+      if isinstance(image_arrays, torch.Tensor) and image_arrays.dtype == torch.uint8 and \
+          (image_arrays.is_cuda or image_arrays.is_pinned()):
         batch = image_arrays
       else:
-        batch = torch.as_tensor(np.ascontiguousarray(np.stack(image_arrays)), dtype=torch.uint8)
-      raw = batch.to(self.device, non_blocking=True)
-      scale = ops.preprocess(raw, eng.input, self.mean_rgb, self.stddev_rgb)
-      self._scales.fill_(scale)
+        # stack into this slot's pinned staging buffer (reused; its last H2D must have finished)
+        if slot['raw_host'] is None or tuple(slot['raw_host'].shape) != shape:
+          slot['raw_host'] = torch.empty(shape, dtype=torch.uint8).pin_memory()
+        slot['ev_h2d'].synchronize()
+        host = slot['raw_host'].numpy()
+        if isinstance(image_arrays, torch.Tensor):
+          host[...] = image_arrays.to(torch.uint8).numpy()
+        else:
+          for i, im in enumerate(image_arrays):
+            host[i] = im
+        batch = slot['raw_host']
+      if slot['raw_dev'] is None or tuple(slot['raw_dev'].shape) != shape:
+        slot['raw_dev'] = torch.empty(shape, dtype=torch.uint8, device=self.device)
+      with torch.cuda.stream(self._copy_stream):
+        self._copy_stream.wait_event(slot['ev_raw_free'])   # pre-process of the request before last
+        slot['raw_dev'].copy_(batch, non_blocking=True)
+        slot['ev_h2d'].record(self._copy_stream)
+      main.wait_event(slot['ev_h2d'])
+      scale = ops.preprocess(slot['raw_dev'], eng.input, self.mean_rgb, self.stddev_rgb)
+      slot['ev_raw_free'].record(main)
+      slot['scales'].fill_(scale)
     else:  # ragged batch: one pre-process launch per image (like the reference's python loop)
       for i, im in enumerate(image_arrays):
         raw = torch.as_tensor(np.ascontiguousarray(im), dtype=torch.uint8).to(self.device)[None]
-        self._scales[i] = ops.preprocess(raw, eng.input[i:i + 1], self.mean_rgb, self.stddev_rgb)
-    eng.image_scales.copy_(self._scales, non_blocking=True)
+        slot['scales'][i] = ops.preprocess(raw, eng.input[i:i + 1], self.mean_rgb, self.stddev_rgb)
+    eng.image_scales.copy_(slot['scales'], non_blocking=True)
+
+  def submit(self, image_arrays):
+    """Enqueues one request and returns a handle; `handle.result()` blocks until its detections
+    are in host memory.  Up to two requests are in flight: the H2D copy and pre-process of
+    request i+1 and the NMS + D2H copy of request i-1 overlap the network of request i (copy
+    stream, main stream, the engine's NMS stream).  Submitting a third request first completes
+    the oldest one."""
+    if getattr(self, '_engines', None) is None:
+      self.build()
+    n = len(image_arrays)
+    if self.batch_size and n != self.batch_size:
+      raise ValueError('expected %d images, got %d' % (self.batch_size, n))
+    if n < 1:
+      raise ValueError('empty request')
+    with torch.cuda.device(self.device):
+      eng = self._engine_for(n)
+      slot = self._slots[n][self._seq % 2]
+      self._seq += 1
+      if slot['pending'] is not None:
+        slot['pending']._finish()          # its host buffer is about to be reused
+      self._stage_raw(eng, slot, image_arrays)
+
+      def after_nms(det, slot=slot):
+        """On the engine's NMS stream right after NMS: all-gather (multi-GPU) + D2H copy."""
+        det = parallel.gather_detections(det, slot['gathered'])
+        slot['host_det'].copy_(det, non_blocking=True)
+        slot['ev_done'].record(torch.cuda.current_stream())
+      eng.run(postprocess=True, after_nms=after_nms)
+    handle = _Request(slot)
+    slot['pending'] = handle
+    return handle
 
   def serve_images(self, image_arrays):
     """image_arrays: list (or array) of HxWx3 uint8 images -> float32 [N, max_output_size, 7].
@@ -154,21 +246,19 @@ class ServingDriver(object):
     Under torch.distributed (one process per GPU, batch sharded over the ranks) the per-rank
     detection blocks are all-gathered on the device first, so every rank returns the global
     [world * N, max_output_size, 7] result (the single collective of the path)."""
-    if self.engine is None:
-      self.build()
-    with torch.cuda.device(self.device):
-      self._stage_raw(image_arrays)
-      self.engine.run(postprocess=True, after_nms=self._gather_and_copy)
-      self.engine.wait_detections()
-      torch.cuda.current_stream().synchronize()
-    return self._host_det.numpy().copy()
+    return self.submit(image_arrays).result()
 
-  def _gather_and_copy(self, det):
-    """Runs on the engine's NMS stream right after NMS: all-gather (multi-GPU) + D2H copy."""
-    det = parallel.gather_detections(det, self._gathered)
-    if det.shape[0] != self._host_det.shape[0]:
-      self._host_det = torch.empty(tuple(det.shape)).pin_memory()
-    self._host_det.copy_(det, non_blocking=True)
+  def serve_stream(self, batches):
+    """Generator over an iterable of requests: yields the detections of each, in order, keeping
+    two requests in flight."""
+    prev = None
+    for batch in batches:
+      cur = self.submit(batch)
+      if prev is not None:
+        yield prev.result()
+      prev = cur
+    if prev is not None:
+      yield prev.result()
 
   def serve_files(self, image_files):
     """image_files: list of encoded image bytes (jpeg/png)."""
@@ -178,7 +268,7 @@ class ServingDriver(object):
 
   def benchmark(self, image_arrays, trace_filename=None):
     """1 warm-up run then the mean of 10 runs, printed like the reference (:500-524)."""
-    if self.engine is None:
+    if self._engines is None:
       self.build()
     self.serve_images(image_arrays)
     start = time.perf_counter()
@@ -187,7 +277,7 @@ class ServingDriver(object):
     end = time.perf_counter()
     inference_time = (end - start) / 10
     print('Per batch inference time: ', inference_time)
-    print('FPS: ', self.batch_size / inference_time)
+    print('FPS: ', len(image_arrays) / inference_time)
     if trace_filename:
       raise NotImplementedError('chrome traces are replaced by ncu / CUDA events (see bench.py)')
     return inference_time

@@ -102,3 +102,58 @@ def test_generate_detections_per_class_path():
   np.testing.assert_array_equal(flipped[..., 3], ow[:, None] - det[..., 1])
   t = postprocess.transform_detections(torch.from_numpy(det)).numpy()
   np.testing.assert_array_equal(t[..., 3], det[..., 3] - det[..., 1])
+
+
+def test_pipelined_submit_equals_synchronous_serving():
+  """submit()/result() keeps two requests in flight (H2D + pre-process of request i+1 and NMS +
+  D2H of request i-1 overlap the network of request i): results must equal the synchronous
+  serve_images() of the same batches, in order, also when slots are reused."""
+  from automl_b200 import inference
+  rng = np.random.default_rng(2)
+  batches = [[rng.integers(0, 256, size=(96, 128, 3), dtype=np.uint8) for _ in range(2)] for _ in range(5)]
+  driver = inference.ServingDriver('efficientdet-d0', '_', batch_size=2,
+                                   model_params={'image_size': 128})
+  expect = [driver.serve_images(b) for b in batches]
+  handles = []
+  got = []
+  for b in batches:                     # never more than two un-collected handles
+    handles.append(driver.submit(b))
+    if len(handles) == 2:
+      got.append(handles.pop(0).result())
+  got.append(handles.pop(0).result())
+  for g, e in zip(got, expect):
+    np.testing.assert_array_equal(g, e)
+  # a third submit completes the oldest request by itself
+  h = [driver.submit(b) for b in batches[:3]]
+  np.testing.assert_array_equal(h[0].result(), expect[0])
+  np.testing.assert_array_equal(h[2].result(), expect[2])
+  np.testing.assert_array_equal(h[1].result(), expect[1])
+  assert [r.shape for r in driver.serve_stream(batches)] == [(2, 100, 7)] * 5
+  for g, e in zip(driver.serve_stream(iter(batches)), expect):
+    np.testing.assert_array_equal(g, e)
+  # pinned uint8 tensors are uploaded without the host staging copy
+  pinned = torch.from_numpy(np.stack(batches[3])).pin_memory()
+  np.testing.assert_array_equal(driver.serve_images(pinned), expect[3])
+
+
+def test_dynamic_batch_and_channels_first():
+  """batch_size=None (reference inference.py:68-109): any number of images per request; and a
+  channels_first config through the driver (inference.py:456-457) gives the same detections."""
+  from automl_b200 import inference
+  rng = np.random.default_rng(4)
+  imgs = [rng.integers(0, 256, size=(80, 100, 3), dtype=np.uint8) for _ in range(3)]
+  fixed = inference.ServingDriver('efficientdet-d0', '_', batch_size=3, model_params={'image_size': 128})
+  ref = fixed.serve_images(imgs)
+  dyn = inference.ServingDriver('efficientdet-d0', '_', batch_size=None, model_params={'image_size': 128})
+  np.testing.assert_array_equal(dyn.serve_images(imgs), ref)
+  one = dyn.serve_images(imgs[1:2])
+  assert one.shape == (1, 100, 7)
+  np.testing.assert_array_equal(one[0, :, 1:], ref[1, :, 1:])     # same image, image id 0 instead of 1
+  cf = inference.ServingDriver('efficientdet-d0', '_', batch_size=3,
+                               model_params={'image_size': 128, 'data_format': 'channels_first'})
+  np.testing.assert_array_equal(cf.serve_images(imgs), ref)
+  # ragged request: images of different sizes are pre-processed one by one
+  ragged = [imgs[0], rng.integers(0, 256, size=(60, 90, 3), dtype=np.uint8), imgs[2]]
+  out = dyn.serve_images(ragged)
+  np.testing.assert_array_equal(out[0], ref[0])
+  np.testing.assert_array_equal(out[2], ref[2])
