@@ -28,6 +28,8 @@ class FuseInput(ctypes.Structure):
 SIGNATURES = {
     'edet_version': (c_int, []),
     'edet_last_error': (ctypes.c_char_p, []),
+    'edet_set_option': (c_int, [ctypes.c_char_p, c_int]),
+    'edet_get_option': (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int)]),
     'edet_device_info': (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     'edet_preprocess': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 ctypes.POINTER(c_float), ctypes.POINTER(c_float),

@@ -15,6 +15,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<int> g_opt_dw_impl{0};
+int option_dw_impl() { return g_opt_dw_impl.load(std::memory_order_relaxed); }
+
 int current_device() {
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
@@ -64,7 +67,28 @@ unsigned* next_sched_slot() {
 }  // namespace pwtc
 }  // namespace edet
 
-extern "C" int edet_version(void) { return 100; }
+extern "C" int edet_version(void) { return 200; }
+extern "C" int edet_set_option(const char* name, int value) {
+  using namespace edet;
+  EDET_CHECK_ARG(name != nullptr, "set_option: null name");
+  if (strcmp(name, "dw_impl") == 0) {
+    EDET_CHECK_ARG(value >= 0 && value <= 2, "set_option: dw_impl must be 0, 1 or 2");
+    g_opt_dw_impl.store(value);
+    return EDET_OK;
+  }
+  set_error("set_option: unknown option '%s'", name);
+  return EDET_ERR_INVALID;
+}
+extern "C" int edet_get_option(const char* name, int* value) {
+  using namespace edet;
+  EDET_CHECK_ARG(name != nullptr && value != nullptr, "get_option: null pointer");
+  if (strcmp(name, "dw_impl") == 0) {
+    *value = option_dw_impl();
+    return EDET_OK;
+  }
+  set_error("get_option: unknown option '%s'", name);
+  return EDET_ERR_INVALID;
+}
 extern "C" const char* edet_last_error(void) { return edet::g_err; }
 extern "C" int edet_device_info(int* sm_count, int* cc) {
   int dev = 0, sms = 0, major = 0, minor = 0;

@@ -171,6 +171,8 @@ inline cudaStream_t as_stream(edet_stream_t s) { return reinterpret_cast<cudaStr
 // one process may drive several engines on several GPUs (Engine(device=...)), so a process-wide
 // static would hand cuda:1 the SM count, scheduler-counter address and shared-memory opt-in
 // state of cuda:0.
+// Library options (edet_set_option): implementation switches for A/B measurements.
+int option_dw_impl();   // 0 auto (tiled kernel where eligible), 1 register kernel only, 2 = 0
 constexpr int kMaxDevices = 64;
 int current_device();                 // ordinal of the current device, -1 (+ error text) on failure
 int device_sm_count();                // multiprocessor count of the current device, 0 on failure

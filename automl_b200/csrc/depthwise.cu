@@ -316,6 +316,11 @@ static int launch_dw(const __half* in, __half* out, const __half* w, const float
   return EDET_OK;
 }
 
+namespace dwt {   // depthwise_tile.cu
+bool eligible(int h, int wd, int c, int k, int stride);
+int run(const __half* in, __half* out, const __half* w, const float* bias, long long* se_sum,
+        int n, int h, int wd, int c, int k, int stride, int act, cudaStream_t stream);
+}  // namespace dwt
 }  // namespace edet
 
 extern "C" int edet_depthwise_conv(const edet_half* in, edet_half* out, const edet_half* w,
@@ -331,6 +336,9 @@ extern "C" int edet_depthwise_conv(const edet_half* in, edet_half* out, const ed
   __half* ho = reinterpret_cast<__half*>(out);
   long long* sp = reinterpret_cast<long long*>(se_sum);
   cudaStream_t s = as_stream(stream);
+  // large maps: TMA-staged shared-memory tiles (depthwise_tile.cu); small maps: register tiles
+  if (option_dw_impl() != 1 && dwt::eligible(h, wd, c, k, stride))
+    return dwt::run(hi, ho, hw, bias, sp, n, h, wd, c, k, stride, act, s);
   if (k == 3 && stride == 1) return launch_dw<3, 1>(hi, ho, hw, bias, sp, n, h, wd, c, act, s);
   if (k == 3 && stride == 2) return launch_dw<3, 2>(hi, ho, hw, bias, sp, n, h, wd, c, act, s);
   if (k == 5 && stride == 1) return launch_dw<5, 1>(hi, ho, hw, bias, sp, n, h, wd, c, act, s);

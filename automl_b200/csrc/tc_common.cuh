@@ -217,7 +217,7 @@ inline int make_map(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1,
 // 4-D half tensor [d3][d2][d1][d0] (NHWC activations: d0 = C, d1 = W, d2 = H, d3 = N), box
 // [1][box2][box1][box0]; swizzle follows box0 (64 / 32 / 16 halves -> 128B / 64B / 32B).
 inline int make_map4(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
-                     uint64_t d3, uint32_t box0, uint32_t box1, uint32_t box2) {
+                     uint64_t d3, uint32_t box0, uint32_t box1, uint32_t box2, bool swizzle = true) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -227,7 +227,9 @@ inline int make_map4(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1
   cuuint64_t strides[3] = {d0 * 2, d0 * d1 * 2, d0 * d1 * d2 * 2};
   cuuint32_t box[4] = {box0, box1, box2, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUtensorMapSwizzle swz = box0 == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+  // swizzle == false: dense [box2][box1][box0] tile (pixel rows of box0 halves, no XOR pattern)
+  const CUtensorMapSwizzle swz = !swizzle      ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                 : box0 == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : box0 == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
                                               : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides,

@@ -28,6 +28,17 @@ def _ptr(t, dtype=None):
   return ctypes.c_void_p(t.data_ptr())
 
 
+def set_option(name, value):
+  """Process-wide implementation switch (A/B measurements, tests): see edet_set_option."""
+  _lib.call('edet_set_option', name.encode(), int(value))
+
+
+def get_option(name):
+  v = ctypes.c_int(0)
+  _lib.call('edet_get_option', name.encode(), ctypes.byref(v))
+  return v.value
+
+
 def preprocess(raw, out, mean_rgb, stddev_rgb):
   """raw uint8 [N,h,w,3] -> out fp32 [N,H,W,3]; returns image_scale_to_original (float)."""
   n, h, w, _ = raw.shape

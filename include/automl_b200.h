@@ -56,6 +56,11 @@ enum {
 
 int edet_version(void);
 const char* edet_last_error(void);
+/* Process-wide implementation switches, for A/B measurements and tests only (results are the same
+ * for every setting).  Options: "dw_impl" = 0 (default: TMA-tiled depthwise kernel where eligible,
+ * register-tiled kernel otherwise) | 1 (register-tiled kernel only). */
+int edet_set_option(const char* name, int value);
+int edet_get_option(const char* name, int* value);
 /* Number of SMs / compute capability of the current device (major*10+minor). */
 int edet_device_info(int* sm_count, int* cc);
 

@@ -92,6 +92,16 @@ DW_CASES = [
     (1, 5, 5, 64, 3, 1, utils.ACT_NONE, False, False),
     (1, 64, 64, 1152, 5, 1, utils.ACT_SWISH, True, True),
     (1, 12, 12, 672, 5, 2, utils.ACT_RELU6, True, False),
+    # maps large enough for the TMA-tiled kernel (depthwise_tile.cu): ragged tiles in x and y,
+    # channel counts that are not multiples of the 64-channel slice, every (k, stride)
+    (2, 50, 70, 144, 3, 1, utils.ACT_SWISH, True, True),
+    (1, 67, 45, 240, 5, 1, utils.ACT_SWISH, True, True),
+    (2, 61, 83, 96, 3, 2, utils.ACT_SWISH, True, True),
+    (1, 97, 59, 144, 5, 2, utils.ACT_SWISH, True, True),
+    (3, 48, 48, 64, 3, 1, utils.ACT_NONE, False, False),    # head depthwise at level 3 size
+    (1, 80, 80, 672, 5, 1, utils.ACT_RELU6, True, True),
+    (1, 160, 160, 72, 5, 2, utils.ACT_RELU6, True, False),  # c % 16 != 0
+    (2, 33, 200, 480, 3, 1, utils.ACT_NONE, True, False),   # many work units per CTA (ring wrap)
 ]
 
 
@@ -127,6 +137,39 @@ def test_depthwise_conv(case):
                        bias.to(DEV) if has_bias else None, act, k, s, again)
     torch.cuda.synchronize()
     assert torch.equal(again, partial)
+
+
+@pytest.mark.parametrize('case', [c for c in DW_CASES if c[1] >= 48 and c[3] >= 64])
+def test_depthwise_tiled_equals_register_kernel(case):
+  """The two depthwise implementations (TMA-tiled / register-tiled) do the same fp32 arithmetic in
+  the same order: their fp16 outputs are bit-identical and the SE sums agree to the fixed-point
+  rounding of the per-thread partial sums."""
+  ops = _ops()
+  n, h, w, c, k, s, act, has_bias, has_se = case
+  g = torch.Generator().manual_seed(7 + h + c)
+  x = torch.randn(n, h, w, c, generator=g).half().to(DEV)
+  wk = (torch.randn(k * k, c, generator=g) / k).half().to(DEV)
+  bias = (torch.randn(c, generator=g) * 0.1).to(DEV) if has_bias else None
+  ho, wo = -(-h // s), -(-w // s)
+  outs, sums = [], []
+  try:
+    for impl in (0, 1):
+      ops.set_option('dw_impl', impl)
+      assert ops.get_option('dw_impl') == impl
+      out = torch.empty(n, ho, wo, c, dtype=torch.float16, device=DEV)
+      part = torch.zeros(n, c, dtype=torch.int64, device=DEV) if has_se else None
+      ops.depthwise_conv(x, out, wk, bias, act, k, s, part)
+      torch.cuda.synchronize()
+      outs.append(out)
+      sums.append(part)
+  finally:
+    ops.set_option('dw_impl', 0)
+  assert torch.equal(outs[0], outs[1])
+  if has_se:
+    # each partial sum is rounded to 2^-20 once: |difference| <= (number of partial sums) * 2^-20
+    assert int((sums[0] - sums[1]).abs().max()) <= ho * wo
+    np.testing.assert_allclose(sums[0].cpu().double().numpy(), sums[1].cpu().double().numpy(),
+                               rtol=1e-5, atol=64)
 
 
 # n, h, w, cin, cmid, k, stride, act, has_se   (D0 blocks 1-5 shapes at small sizes + edge cases)
