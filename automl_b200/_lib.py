@@ -73,6 +73,10 @@ SIGNATURES = {
 _lib = None
 
 
+class EdetError(RuntimeError):
+  pass
+
+
 def load():
   """Loads libautoml_b200.so (raises RuntimeError when it is missing: build it first with
   `python -m automl_b200.build` / __graft_entry__.build())."""
@@ -89,11 +93,12 @@ def load():
     fn.restype = restype
     fn.argtypes = argtypes
   _lib = lib
+  # A/B switches from the environment (scripts/, bench.py runs): EDET_DW_IMPL, EDET_PW_TEAMS
+  for env, opt in (('EDET_DW_IMPL', b'dw_impl'), ('EDET_PW_TEAMS', b'pw_teams')):
+    if os.environ.get(env):
+      if lib.edet_set_option(opt, int(os.environ[env])) != 0:
+        raise EdetError('bad %s=%s' % (env, os.environ[env]))
   return lib
-
-
-class EdetError(RuntimeError):
-  pass
 
 
 def check(rc):

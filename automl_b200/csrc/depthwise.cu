@@ -235,7 +235,10 @@ se_fc1_kernel(const long long* __restrict__ se_sum, float inv_hw, const float* _
 // image):
 //   gate[n][c]            = sigmoid(b2[c] + sum_j w2t[j][c] * hidden[n][j])
 //   wt_scaled[n][o][c]    = wt[o][c] * gate[n][c]
+// blockIdx.z splits the output rows (kSeRows per CTA) so that small batches still fill the chip
+// (D7x at batch 2: 640 x 3840 weights per image); every z recomputes the cheap gate slice.
 constexpr int kSeSlice = 128;
+constexpr int kSeRows = 64;
 __global__ void __launch_bounds__(256)
 se_fc2_scale_kernel(const float* __restrict__ hidden, const float* __restrict__ w2t,
                     const float* __restrict__ b2, float* __restrict__ gate,
@@ -267,7 +270,7 @@ se_fc2_scale_kernel(const float* __restrict__ hidden, const float* __restrict__ 
       }
       for (; j < se; ++j) s0 = fmaf(__ldg(w2t + static_cast<size_t>(j) * c + ch), hid[j], s0);
       v = 1.0f / (1.0f + expf(-((s0 + s1) + (s2 + s3))));
-      gate[static_cast<size_t>(n) * c + ch] = v;
+      if (blockIdx.z == 0) gate[static_cast<size_t>(n) * c + ch] = v;
     }
     g[threadIdx.x] = v;
   }
@@ -280,8 +283,9 @@ se_fc2_scale_kernel(const float* __restrict__ hidden, const float* __restrict__ 
   const float4 g0 = *reinterpret_cast<const float4*>(g + piece * 8);
   const float4 g1 = *reinterpret_cast<const float4*>(g + piece * 8 + 4);
   __half* dst = wt_scaled + static_cast<size_t>(n) * nout * c;
+  const int o_end = min(nout, static_cast<int>(blockIdx.z + 1) * kSeRows);
 #pragma unroll 4
-  for (int o = row0; o < nout; o += 16) {
+  for (int o = static_cast<int>(blockIdx.z) * kSeRows + row0; o < o_end; o += 16) {
     float f[8];
     half8_to_float(__ldg(reinterpret_cast<const uint4*>(wt + static_cast<size_t>(o) * c + ch)), f);
     f[0] *= g0.x; f[1] *= g0.y; f[2] *= g0.z; f[3] *= g0.w;
@@ -360,7 +364,8 @@ extern "C" int edet_se_fc(const int64_t* se_sum, float inv_hw, const float* w1, 
                              0, as_stream(stream), reinterpret_cast<const long long*>(se_sum),
                              inv_hw, w1, b1, hidden, reinterpret_cast<long long*>(zero_buf),
                              static_cast<long long>(n) * zero_count, n, c, se, act));
-  EDET_CHECK_CUDA(launch_pdl(se_fc2_scale_kernel, dim3(ceil_div(c, kSeSlice), n), dim3(256), smem,
+  EDET_CHECK_CUDA(launch_pdl(se_fc2_scale_kernel,
+                             dim3(ceil_div(c, kSeSlice), n, wt ? ceil_div(nout, kSeRows) : 1), dim3(256), smem,
                              as_stream(stream), static_cast<const float*>(hidden), w2, b2, gate,
                              reinterpret_cast<const __half*>(wt),
                              reinterpret_cast<__half*>(wt_scaled), c, se, nout));

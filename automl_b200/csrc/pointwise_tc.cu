@@ -24,8 +24,19 @@
 namespace edet {
 namespace pwtc {
 
-constexpr int kThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
-constexpr int kEpiThreads = 256;
+// warp 0 TMA, warp 1 MMA, then TEAMS x 4 epilogue warps (one per TMEM lane quarter and team):
+//   TEAMS == 2: 320 threads, <= 96 registers; every 64-column store chunk is split between the
+//               two teams' staging slabs (4 KiB each)
+//   TEAMS == 3: 448 threads, <= 72 registers; the unit of epilogue work is 32 columns (one
+//               2 KiB [32 rows x 32 cols] TMA store), handed to the teams round robin -- 50 % more
+//               warps to hide the MUFU / dependent-issue latency of the swish epilogue, balanced
+//               for the expand widths (N = 96, 144, 240 and tiles of 96)
+template <int TEAMS>
+struct Epi {
+  static constexpr int kWarps = 4 * TEAMS;
+  static constexpr int kThreads = 64 + 32 * kWarps;
+  static constexpr int kSlabBytes = TEAMS == 2 ? 4096 : 2048;
+};
 constexpr int kStoreCols = 64;
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 113 * 1024;                    // two CTAs per SM share the 227 KiB
@@ -57,8 +68,8 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const Params& p) {
   return c;
 }
 
-template <int ACT, bool HAS_RES>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int ACT, bool HAS_RES, int TEAMS>
+__global__ void __launch_bounds__(Epi<TEAMS>::kThreads, 2)
 pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                     const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_o, const Params p) {
@@ -69,7 +80,9 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   uint8_t* smem_store = smem + p.num_stages * stage_bytes;
-  float* smem_bias = reinterpret_cast<float*>(smem_store + p.slabs_per_warp * (kEpiThreads / 32) * 4096);
+  constexpr int kEpiWarps = Epi<TEAMS>::kWarps;
+  constexpr int kSlabBytes = Epi<TEAMS>::kSlabBytes;
+  float* smem_bias = reinterpret_cast<float*>(smem_store + p.slabs_per_warp * kEpiWarps * kSlabBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + 2 * 256);
   uint64_t* full_bar = bars;                       // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]
@@ -87,7 +100,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[s]), kEpiThreads / 32);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tmem_empty_bar[s]), kEpiWarps);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -172,7 +185,8 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       }
     }
   } else {
-    // ===================== Epilogue (warps 2..9) =====================
+    // ===================== Epilogue =====================
+    if constexpr (TEAMS == 2) {
     // Fully decoupled warps: warp (quarter, team) owns rows quarter*32..+31 of the tile and the
     // 64-column store chunks c == team (mod 2).  Each warp has a private 4 KiB staging slab and
     // issues its own TMA stores ([32 rows x 64 cols] boxes), so the only synchronisation in the
@@ -282,6 +296,113 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
         }
       }
     }
+    } else {
+      // Units of 32 columns: warp (quarter, team) owns rows quarter*32..+31 of the tile and the
+      // units u == team (mod TEAMS).  Each warp has private 2 KiB staging slabs ([32 rows] x 64
+      // bytes, 64B-swizzled) and issues its own [32 x 32] TMA stores; the only synchronisation is
+      // the TMEM full / empty handshake with the MMA warp.
+      const int e_warp = warp - 2;
+      const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+      const int team = e_warp >> 2;
+      const int row_in_tile = quarter * 32 + lane;
+      uint8_t* my_slabs = smem_store + e_warp * p.slabs_per_warp * kSlabBytes;
+      int iter = 0;
+      int store_cnt = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++iter) {
+        const TileCoord tc = decode_tile(t, p);
+        const int as = p.accum_stages == 2 ? (iter & 1) : 0;
+        const uint32_t aphase = p.accum_stages == 2 ? ((iter >> 1) & 1) : (iter & 1);
+        const int n0 = tc.n_blk * p.block_n;
+        const int row = tc.m_blk * BLOCK_M + row_in_tile;
+        const bool row_ok = row < p.rows;
+        const __half* res_row = nullptr;
+        if (HAS_RES) {
+          res_row = p.residual + (static_cast<size_t>(tc.b) * p.rows + (row_ok ? row : 0)) * p.ldr;
+        }
+        mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
+        tc_fence_after();
+        const int n_valid = min(p.block_n, ((p.nout - n0 + 15) >> 4) << 4);
+        const int num_units = (n_valid + 31) >> 5;
+        int my_last = -1;
+        for (int u = team; u < num_units; u += TEAMS) my_last = u;
+        if (my_last < 0) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+        }
+        for (int u = team; u < num_units; u += TEAMS) {
+          const int cols = min(32, n_valid - u * 32);      // 16 or 32
+          uint8_t* my_stage = my_slabs + (p.slabs_per_warp == 2 ? (store_cnt & 1) * kSlabBytes : 0);
+          ++store_cnt;
+          if (lane == 0) {                        // the store that last used this slab has left it
+            if (p.slabs_per_warp == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+          }
+          __syncwarp();
+          const uint32_t row_base = smem_u32(my_stage) + lane * 64;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                 static_cast<uint32_t>(as * p.block_n + u * 32);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (g * 16 < cols) {
+              float v[16];
+              tc_ld16(taddr + g * 16, v);
+              tc_wait_ld();
+              if (u == my_last && (g == 1 || cols == 16)) {
+                // all TMEM reads of this warp for this accumulator are done
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+              }
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                const int col = n0 + u * 32 + g * 16 + jj * 8;
+                float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                if (col < p.nout_pad8) {          // a whole group of 8 biases is in bounds
+                  b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                  b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                } else if (col < p.nout) {        // ragged last group (nout % 8 != 0)
+                  float bb[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) bb[e] = (col + e < p.nout) ? __ldg(p.bias + col + e) : 0.f;
+                  b0 = make_float4(bb[0], bb[1], bb[2], bb[3]);
+                  b1 = make_float4(bb[4], bb[5], bb[6], bb[7]);
+                }
+                float2 o2[4];
+                o2[0] = __fadd2_rn(make_float2(v[jj * 8 + 0], v[jj * 8 + 1]), make_float2(b0.x, b0.y));
+                o2[1] = __fadd2_rn(make_float2(v[jj * 8 + 2], v[jj * 8 + 3]), make_float2(b0.z, b0.w));
+                o2[2] = __fadd2_rn(make_float2(v[jj * 8 + 4], v[jj * 8 + 5]), make_float2(b1.x, b1.y));
+                o2[3] = __fadd2_rn(make_float2(v[jj * 8 + 6], v[jj * 8 + 7]), make_float2(b1.z, b1.w));
+                apply_act4<ACT>(o2[0], o2[1]);
+                apply_act4<ACT>(o2[2], o2[3]);
+                float o[8] = {o2[0].x, o2[0].y, o2[1].x, o2[1].y, o2[2].x, o2[2].y, o2[3].x, o2[3].y};
+                if (HAS_RES) {
+                  if (row_ok && col < p.nout) {
+                    float r[8];
+                    half8_to_float(ldg_nc_v4(res_row + col), r);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] += r[e];
+                  }
+                }
+                const uint4 packed = float_to_half8(o);
+                const int chunk16 = g * 2 + jj;    // 16-byte piece inside the 64-byte row
+                // 64B swizzle: the 16-byte piece index is XORed with bits [7:8] of the address
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                                 row_base + (((chunk16 ^ ((lane >> 1) & 3))) << 4)),
+                             "r"(packed.x), "r"(packed.y), "r"(packed.z), "r"(packed.w)
+                             : "memory");
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_o, smem_u32(my_stage), n0 + u * 32, tc.m_blk * BLOCK_M + quarter * 32,
+                         tc.b);
+            tma_store_commit();
+          }
+        }
+      }
+    }
     if (lane == 0) tma_store_wait_all();
   }
 
@@ -303,19 +424,21 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
 //                 into two double-buffered tiles measured 1.5 % slower on the D0 step);
 //   wider       : tiles of 128 columns; the A tile of the extra tiles comes from L2 and the
 //                 epilogue skips the columns past nout.
-static int pick_block_n(int nout) {
+// With three epilogue teams (32-column units) wide layers use tiles of 96 columns (3 units).
+static int pick_block_n(int nout, int teams) {
   if (nout <= 128) return ((nout + 15) / 16) * 16;
   if (nout <= 256) return ((nout + 15) / 16) * 16;
-  return 128;
+  return teams == 3 ? 96 : 128;
 }
 
-template <int ACT, bool HAS_RES>
+template <int ACT, bool HAS_RES, int TEAMS>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo,
                   const Params& p, int grid, int smem_bytes, cudaStream_t stream) {
-  auto kern = pointwise_tc_kernel<ACT, HAS_RES>;
+  auto kern = pointwise_tc_kernel<ACT, HAS_RES, TEAMS>;
   static int configured[kMaxDevices];   // per instantiation and device; no API call once set
   if (int rc = ensure_dynamic_smem(kern, kSmemLimit, configured)) return rc;
-  EDET_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem_bytes, stream, ma, mw, mo, p));
+  EDET_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(Epi<TEAMS>::kThreads), smem_bytes, stream, ma,
+                             mw, mo, p));
   return EDET_OK;
 }
 
@@ -328,7 +451,13 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   p.k = k;
   p.nout = nout;
   p.nout_pad8 = nout & ~7;   // whole float4 pairs of bias that are in bounds
-  p.block_n = pick_block_n(nout);
+  // Epilogue teams: the swish epilogues are bound by MUFU / dependent-issue latency, not bytes, so
+  // they get three teams of four warps (448 threads at <= 72 registers); the linear epilogues
+  // keep two (edet_set_option("pw_teams", 2 | 3) forces one for A/B measurements).
+  const int opt_teams = option_pw_teams();
+  const int teams = opt_teams ? opt_teams : (act == EDET_ACT_SWISH ? 3 : 2);
+  const int epi_warps = 4 * teams, slab_bytes = teams == 2 ? 4096 : 2048;
+  p.block_n = pick_block_n(nout, teams);
   p.num_m_blocks = ceil_div(rows, BLOCK_M);
   p.num_n_blocks = ceil_div(nout, p.block_n);
   // k-block / smem row pitch: 16 halves (32B swizzle) for K <= 16, 32 (64B) for K <= 32, else
@@ -354,7 +483,8 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   // thin stages (small K) leave room for a second store slab per epilogue warp
   p.slabs_per_warp = stage_bytes <= 16 * 1024 ? 2 : 1;
-  const int fixed = p.slabs_per_warp * (kEpiThreads / 32) * 4096 + 2 * 256 * 4 +
+  if (teams == 3) p.slabs_per_warp = 2;
+  const int fixed = p.slabs_per_warp * epi_warps * slab_bytes + 2 * 256 * 4 +
                     (2 * kMaxStages + 4) * 8 + 16;
   int stages = (kSmemLimit - 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -370,7 +500,9 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   if ((rc = make_map(&mw, wt, k, nout, wbatch, k, static_cast<uint64_t>(nout) * k, p.block_n,
                      p.block_k)))
     return rc;
-  if ((rc = make_map(&mo, out, nout, rows, batch, ldo, static_cast<uint64_t>(rows) * ldo, 32)))
+  // store box: [32 rows] x 64 columns (128B swizzle) for two teams, x 32 columns (64B) for three
+  if ((rc = make_map(&mo, out, nout, rows, batch, ldo, static_cast<uint64_t>(rows) * ldo, 32,
+                     teams == 2 ? 64 : 32)))
     return rc;
 
   const int sm_count = device_sm_count();
@@ -378,9 +510,12 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   const int grid = p.total_tiles < 2 * sm_count ? p.total_tiles : 2 * sm_count;
   const bool has_res = residual != nullptr;
 
-#define EDET_PW_CASE(A)                                                              \
-  return has_res ? launch<A, true>(ma, mw, mo, p, grid, smem_bytes, stream)          \
-                 : launch<A, false>(ma, mw, mo, p, grid, smem_bytes, stream)
+#define EDET_PW_CASE(A)                                                                       \
+  if (teams == 3)                                                                             \
+    return has_res ? launch<A, true, 3>(ma, mw, mo, p, grid, smem_bytes, stream)              \
+                   : launch<A, false, 3>(ma, mw, mo, p, grid, smem_bytes, stream);            \
+  return has_res ? launch<A, true, 2>(ma, mw, mo, p, grid, smem_bytes, stream)                \
+                 : launch<A, false, 2>(ma, mw, mo, p, grid, smem_bytes, stream)
   switch (act) {
     case EDET_ACT_NONE: EDET_PW_CASE(EDET_ACT_NONE);
     case EDET_ACT_SWISH: EDET_PW_CASE(EDET_ACT_SWISH);

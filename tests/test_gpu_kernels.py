@@ -81,6 +81,49 @@ def test_pointwise_conv(case, impl_name):
     assert bool(((pad == 7.0) | (pad == 0.0)).all())
 
 
+@pytest.mark.parametrize('case', PW_CASES + [
+    (1, 5000, 16, 96, utils.ACT_SWISH, False, False),      # expand widths: 3 / 5 / 8 units of 32
+    (2, 3000, 24, 144, utils.ACT_SWISH, False, False),
+    (1, 2500, 40, 240, utils.ACT_SWISH, False, False),
+    (1, 1500, 80, 480, utils.ACT_SWISH, False, False),     # tiles of 96 columns with three teams
+    (1, 900, 112, 672, utils.ACT_SWISH, False, False),
+    (1, 300, 64, 88, utils.ACT_SWISH, True, False),        # 88 = 2 units + a 24-column tail (16 + 8)
+])
+def test_pointwise_epilogue_teams_agree(case):
+  """The two epilogue organisations of pointwise_tc_kernel (two teams x 64-column chunks, three
+  teams x 32-column units) read the same accumulators and do the same fp32 epilogue arithmetic:
+  bit-identical outputs."""
+  ops = _ops()
+  batch, rows, k, nout, act, has_res, per_image = case
+  g = torch.Generator().manual_seed(4321 + rows + k + nout)
+  a = torch.randn(batch, rows, k, generator=g).half().to(DEV)
+  wb = batch if per_image else 1
+  w = (torch.randn(wb, nout, k, generator=g) / np.sqrt(k)).half().to(DEV)
+  bias = torch.randn(nout, generator=g).to(DEV)
+  ldo = -(-nout // 8) * 8
+  res = torch.randn(batch, rows, ldo, generator=g).half().to(DEV) if has_res else None
+  outs = []
+  try:
+    for teams in (2, 3):
+      ops.set_option('pw_teams', teams)
+      out = torch.full((batch, rows, ldo), 7.0, dtype=torch.float16, device=DEV)
+      ops.pointwise_conv(a, w if per_image else w[0], bias, out, act, residual=res, rows=rows,
+                         batch=batch, nout=nout)
+      torch.cuda.synchronize()
+      outs.append(out)
+  finally:
+    ops.set_option('pw_teams', 0)
+  assert torch.equal(outs[0], outs[1])
+  ref = torch.einsum('brk,bnk->brn', a.float().cpu().double(), w.float().cpu().double().expand(batch, -1, -1))
+  ref = act_ref(ref + bias.cpu().double(), act)
+  if has_res:
+    ref = ref + res[..., :nout].cpu().double()
+  assert torch.allclose(outs[1][..., :nout].cpu().double(), ref, rtol=2e-3, atol=2e-3)
+  if ldo > nout:   # pad columns: untouched, or zeros from the 16-byte granular TMA store
+    pad = outs[1][..., nout:]
+    assert bool(((pad == 7.0) | (pad == 0.0)).all())
+
+
 # ---------------------------------------------------------------------------------------------
 DW_CASES = [
     # n, h, w, c, k, s, act, bias, se
