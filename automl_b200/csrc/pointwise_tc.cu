@@ -451,11 +451,12 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   p.k = k;
   p.nout = nout;
   p.nout_pad8 = nout & ~7;   // whole float4 pairs of bias that are in bounds
-  // Epilogue teams: the swish epilogues are bound by MUFU / dependent-issue latency, not bytes, so
-  // they get three teams of four warps (448 threads at <= 72 registers); the linear epilogues
-  // keep two (edet_set_option("pw_teams", 2 | 3) forces one for A/B measurements).
+  // Epilogue teams: three teams of four warps (448 threads at <= 72 registers) by default -- the
+  // epilogues are bound by MUFU / dependent-issue latency, not bytes, and 50 % more warps hide it
+  // (measured on the D0 step: 4.68 ms with two teams, 4.53 ms with three, all layers);
+  // edet_set_option("pw_teams", 2 | 3) forces a variant for A/B measurements.
   const int opt_teams = option_pw_teams();
-  const int teams = opt_teams ? opt_teams : (act == EDET_ACT_SWISH ? 3 : 2);
+  const int teams = opt_teams ? opt_teams : 3;
   const int epi_warps = 4 * teams, slab_bytes = teams == 2 ? 4096 : 2048;
   p.block_n = pick_block_n(nout, teams);
   p.num_m_blocks = ceil_div(rows, BLOCK_M);

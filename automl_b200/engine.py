@@ -11,6 +11,7 @@ The launch list mirrors the call structure of efficientdet_arch.efficientdet
 (inference.py:233-271).  PyTorch is used for device memory, streams and graph capture only.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -67,6 +68,8 @@ class Engine(object):
     self.pw_impl = pw_impl
     self.use_cuda_graph = use_cuda_graph
     self.image_id_base = image_id_base
+    if os.environ.get('EDET_FUSE_FRONT'):     # A/B switch for scripts / bench runs
+      fuse_mbconv_front = os.environ['EDET_FUSE_FRONT'] != '0'
     self.fuse_mbconv_front = fuse_mbconv_front
     self.fuse_sepconv = fuse_sepconv              # head tower layers: dw + pw in one kernel
     self.fuse_sepconv_nodes = fuse_sepconv_nodes  # BiFPN nodes (measured slower than the pair)
