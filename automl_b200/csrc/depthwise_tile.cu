@@ -50,6 +50,7 @@ struct Params {
   const float* bias;      // [c] or null
   __half* out;            // [n, ho, wo, c]
   long long* se_sum;      // [n, c] or null
+  unsigned* sched;        // dynamic work-unit scheduler slot (tc_common.cuh)
 };
 
 struct Unit {
@@ -84,6 +85,7 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * C::TILE_BYTES);      // [NSTAGE]
   unsigned long long* se_s = reinterpret_cast<unsigned long long*>(bars + NSTAGE);  // [2][kCB]
+  volatile int* unit_s = reinterpret_cast<volatile int*>(se_s + 2 * kCB);           // [NSTAGE]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -92,7 +94,6 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
   }
   if (HAS_SE && threadIdx.x < 2 * kCB) se_s[threadIdx.x] = 0ull;
-  __syncthreads();
   pdl_wait_prior();      // everything above overlapped the previous kernel's tail
 
   auto issue = [&](int u, int stage) {       // thread 0 only
@@ -102,12 +103,25 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
     tma_load_4d(smem_u32(smem + stage * C::TILE_BYTES), &map_x, bar, un.chunk * kCB,
                 un.tx * C::TOW * S - p.pad_l, un.ty * C::TOH * S - p.pad_t, un.n);
   };
+  // Work units come from a global counter (CTA i owns unit i, every further unit is fetched):
+  // when another stream holds some SMs (the NMS of the previous batch) late CTAs simply find less
+  // work instead of owning a full static share.  Thread 0 fetches NSTAGE units ahead and parks
+  // each stage's unit index in unit_s; after the first out-of-range fetch it stops fetching.
+  bool exhausted = false;    // thread 0 only
+  auto next_unit = [&]() -> int {
+    if (exhausted) return p.total_units;
+    const int u = sched_next_tile(p.sched, p.total_units);
+    if (u >= p.total_units) exhausted = true;
+    return u;
+  };
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      const int u = blockIdx.x + s * gridDim.x;
+      const int u = s == 0 ? static_cast<int>(blockIdx.x) : next_unit();
+      unit_s[s] = u;
       if (u < p.total_units) issue(u, s);
     }
   }
+  __syncthreads();
 
   const int wx = warp % C::WX, wy = warp / C::WX;
   const int oy_t = wy * TR, ox_t = wx * TC;                      // thread's outputs inside the tile
@@ -119,9 +133,10 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
   float2 bv = make_float2(0.f, 0.f);
   int cur_chunk = -1;
 
-  int it = 0;
-  for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+  for (int it = 0;; ++it) {
     const int stage = it % NSTAGE;
+    const int u = unit_s[stage];
+    if (u >= p.total_units) break;       // same value for every thread of the CTA
     const uint32_t phase = static_cast<uint32_t>(it / NSTAGE) & 1u;
     const Unit un = decode(u, p);
     const int cp = un.chunk * (kCB / 2) + lane;                  // channel pair of this lane
@@ -197,7 +212,8 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
     }
     __syncthreads();       // every thread has finished reading this stage (and adding to se_unit)
     if (threadIdx.x == 0) {
-      const int un_next = u + NSTAGE * gridDim.x;
+      const int un_next = next_unit();
+      unit_s[stage] = un_next;           // read NSTAGE iterations (>= 1 barrier) later
       if (un_next < p.total_units) issue(un_next, stage);
     }
     if (HAS_SE && threadIdx.x < kCB) {
@@ -215,7 +231,7 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
 template <int K, int S>
 static int launch_kernel(const CUtensorMap& mx, const Params& p, int grid, int act, cudaStream_t stream) {
   using C = Cfg<K, S>;
-  const int smem_bytes = 1024 + C::NSTAGE * C::TILE_BYTES + C::NSTAGE * 8 + 2 * kCB * 8;
+  const int smem_bytes = 1024 + C::NSTAGE * C::TILE_BYTES + C::NSTAGE * 8 + 2 * kCB * 8 + 32;
   const bool hb = p.bias != nullptr, hs = p.se_sum != nullptr;
 #define EDET_DWT(ACT, HB, HS)                                                                  \
   do {                                                                                         \
@@ -258,6 +274,8 @@ static int run_ks(const __half* in, __half* out, const __half* w, const float* b
   EDET_CHECK_ARG(total < 0x7fffffffLL, "depthwise(tile): too many work units");
   p.total_units = static_cast<int>(total);
   p.wgt = w; p.bias = bias; p.out = out; p.se_sum = se_sum;
+  p.sched = next_sched_slot();
+  if (!p.sched) return EDET_ERR_CUDA;
   CUtensorMap mx;
   if (int rc = make_map4(&mx, in, c, wd, h, n, kCB, C::TIW, C::TIH, /*swizzle=*/false)) return rc;
   const int sms = device_sm_count();

@@ -39,6 +39,7 @@ struct Epi {
 };
 constexpr int kStoreCols = 64;
 constexpr int kMaxStages = 8;
+constexpr int kRing = 4;          // tile-index ring entries (power of two)
 constexpr int kSmemLimit = 113 * 1024;                    // two CTAs per SM share the 227 KiB
 
 struct Params {
@@ -54,6 +55,7 @@ struct Params {
   int total_tiles;
   const float* bias;
   const __half* residual;
+  unsigned* sched;    // dynamic tile scheduler slot (tc_common.cuh)
 };
 
 struct TileCoord {
@@ -88,7 +90,14 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
   uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]
   uint64_t* tmem_full_bar = bars + 2 * kMaxStages;     // [2]
   uint64_t* tmem_empty_bar = bars + 2 * kMaxStages + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  // Tile indices travel from the producer to the MMA warp and the epilogue warps through a small
+  // ring: CTA i owns tile i, every further tile comes from a global counter (sched_next_tile), so
+  // a CTA that gets its SM late -- another stream's kernel, e.g. the NMS of the previous batch,
+  // was holding it -- simply finds less work instead of owning a full static share.
+  uint64_t* ring_full = bars + 2 * kMaxStages + 4;       // [kRing] producer -> consumers
+  uint64_t* ring_empty = ring_full + kRing;              // [kRing] consumers -> producer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring_empty + kRing);
+  volatile int* tile_ring = reinterpret_cast<volatile int*>(tmem_slot + 4);   // [kRing]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,6 +110,10 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[s]), kEpiWarps);  // one arrive per epilogue warp
+    }
+    for (int s = 0; s < kRing; ++s) {
+      mbar_init(smem_u32(&ring_full[s]), 1);
+      mbar_init(smem_u32(&ring_empty[s]), 1 + kEpiWarps);  // the MMA warp + every epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -121,6 +134,16 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait_prior();          // everything above overlapped the previous kernel's tail
 
+  // consumer side of the tile ring: whole warp (or the single MMA lane) waits, reads, releases
+  auto ring_get = [&](int i, bool whole_warp) -> int {
+    const int slot = i & (kRing - 1);
+    mbar_wait(smem_u32(&ring_full[slot]), static_cast<uint32_t>(i / kRing) & 1u);
+    const int t = tile_ring[slot];
+    if (whole_warp) __syncwarp();
+    if (!whole_warp || lane == 0) mbar_arrive(smem_u32(&ring_empty[slot]));
+    return t;
+  };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -128,7 +151,20 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       uint32_t phase = 0;
       // bytes the two TMA boxes deliver (the B slot may be padded to 1 KiB)
       const uint32_t tx_bytes = static_cast<uint32_t>(p.a_stage_bytes + p.block_n * p.block_k * 2);
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      bool exhausted = false;
+      for (int i = 0;; ++i) {
+        int t = p.total_tiles;
+        if (i == 0) {
+          t = blockIdx.x;
+        } else if (!exhausted) {
+          t = sched_next_tile(p.sched, p.total_tiles);
+          exhausted = t >= p.total_tiles;
+        }
+        const int slot = i & (kRing - 1);
+        mbar_wait(smem_u32(&ring_empty[slot]), (static_cast<uint32_t>(i / kRing) & 1u) ^ 1u);
+        tile_ring[slot] = t;
+        mbar_arrive(smem_u32(&ring_full[slot]));     // release: the index is visible to waiters
+        if (t >= p.total_tiles) break;
         const TileCoord tc = decode_tile(t, p);
         const int wb = (p.wbatch > 1) ? tc.b : 0;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -155,8 +191,8 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                              (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
-      int iter = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++iter) {
+      for (int iter = 0;; ++iter) {
+        if (ring_get(iter, false) >= p.total_tiles) break;
         const int as = p.accum_stages == 2 ? (iter & 1) : 0;
         const uint32_t aphase = p.accum_stages == 2 ? ((iter >> 1) & 1) : (iter & 1);
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1);
@@ -196,9 +232,10 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
     const int team = e_warp >> 2;             // even / odd store chunks
     const int row_in_tile = quarter * 32 + lane;
     uint8_t* my_slabs = smem_store + e_warp * p.slabs_per_warp * (32 * 128);
-    int iter = 0;
     int store_cnt = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++iter) {
+    for (int iter = 0;; ++iter) {
+      const int t = ring_get(iter, true);
+      if (t >= p.total_tiles) break;
       const TileCoord tc = decode_tile(t, p);
       const int as = p.accum_stages == 2 ? (iter & 1) : 0;
       const uint32_t aphase = p.accum_stages == 2 ? ((iter >> 1) & 1) : (iter & 1);
@@ -306,9 +343,10 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       const int team = e_warp >> 2;
       const int row_in_tile = quarter * 32 + lane;
       uint8_t* my_slabs = smem_store + e_warp * p.slabs_per_warp * kSlabBytes;
-      int iter = 0;
       int store_cnt = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++iter) {
+      for (int iter = 0;; ++iter) {
+        const int t = ring_get(iter, true);
+        if (t >= p.total_tiles) break;
         const TileCoord tc = decode_tile(t, p);
         const int as = p.accum_stages == 2 ? (iter & 1) : 0;
         const uint32_t aphase = p.accum_stages == 2 ? ((iter >> 1) & 1) : (iter & 1);
@@ -480,13 +518,15 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   while (cols < p.accum_stages * p.block_n) cols *= 2;
   p.tmem_cols = cols;
   p.total_tiles = batch * p.num_m_blocks * p.num_n_blocks;
+  p.sched = next_sched_slot();
+  if (!p.sched) return EDET_ERR_CUDA;
 
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   // thin stages (small K) leave room for a second store slab per epilogue warp
   p.slabs_per_warp = stage_bytes <= 16 * 1024 ? 2 : 1;
   if (teams == 3) p.slabs_per_warp = 2;
   const int fixed = p.slabs_per_warp * epi_warps * slab_bytes + 2 * 256 * 4 +
-                    (2 * kMaxStages + 4) * 8 + 16;
+                    (2 * kMaxStages + 4 + 2 * kRing) * 8 + 16 + 4 * kRing;
   int stages = (kSmemLimit - 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   EDET_CHECK_ARG(stages >= 2, "pointwise_tc: block_n %d leaves <2 pipeline stages", p.block_n);
