@@ -16,7 +16,11 @@ constexpr int kFuseCB = 32;                // channels per CTA
 // phase-2 loads (4 channel groups x 2 columns) hit 8 distinct bank groups.
 constexpr int kFusePitch = kFuseCB + 4;
 
-template <int ACT>
+// SIG: compile-time input signature (fuse_common.cuh: kSigGeneric or one of the three shapes a
+// BiFPN cell has).  With the modes known at compile time the loads of ALL inputs of an item
+// are issued before any of them is consumed (the generic loop serialises one global round trip
+// per input: the kernel is latency bound, ncu long-scoreboard 5.0 issue-slots per instruction).
+template <int ACT, int SIG>
 __global__ void __launch_bounds__(kFuseThreads)
 fuse_dw_kernel(const FuseParams p, const __half* __restrict__ dw_w, __half* __restrict__ out,
                int h, int wd, int c, int chunks) {
@@ -46,14 +50,39 @@ fuse_dw_kernel(const FuseParams p, const __half* __restrict__ dw_w, __half* __re
     for (int e = 0; e < 4; ++e) acc[e] = make_float2(0.f, 0.f);
     if (g < groups && y >= 0 && y < h && x >= 0 && x < wd) {
       const int ch = c0 + g * 8;
-      for (int i = 0; i < p.n_inputs; ++i) {
-        const FuseIn& fi = p.in[i];
-        const __half* base = fi.ptr + static_cast<size_t>(n) * fi.h * fi.w * c;
-        float v[8];
-        resample8(fi, base, c, y, x, ch, v);
-        const float2 w2 = make_float2(fi.weight, fi.weight);
+      if (SIG == kSigGeneric) {
+        for (int i = 0; i < p.n_inputs; ++i) {
+          const FuseIn& fi = p.in[i];
+          const __half* base = fi.ptr + static_cast<size_t>(n) * fi.h * fi.w * c;
+          float v[8];
+          resample8(fi, base, c, y, x, ch, v);
+          const float2 w2 = make_float2(fi.weight, fi.weight);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] = __ffma2_rn(make_float2(v[2 * e], v[2 * e + 1]), w2, acc[e]);
+          for (int e = 0; e < 4; ++e) acc[e] = __ffma2_rn(make_float2(v[2 * e], v[2 * e + 1]), w2, acc[e]);
+        }
+      } else {
+        // all raw loads first (same values, same accumulation order as the generic loop)
+        constexpr int NI = sig_inputs(SIG);
+        uint4 raw0[9], raw1[9], raw2[9];
+        int taps0 = 0, taps1 = 0, taps2 = 0;
+        auto img = [&](int i) { return p.in[i].ptr + static_cast<size_t>(n) * p.in[i].h * p.in[i].w * c; };
+        taps0 = resample_raw<sig_mode(SIG, 0)>(p.in[0], img(0), c, y, x, ch, raw0);
+        taps1 = resample_raw<sig_mode(SIG, 1)>(p.in[1], img(1), c, y, x, ch, raw1);
+        if (NI == 3) taps2 = resample_raw<sig_mode(SIG, 2)>(p.in[2], img(2), c, y, x, ch, raw2);
+        auto accumulate = [&](const float* v, float weight) {
+          const float2 w2 = make_float2(weight, weight);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[e] = __ffma2_rn(make_float2(v[2 * e], v[2 * e + 1]), w2, acc[e]);
+        };
+        float v[8];
+        resample_reduce<sig_mode(SIG, 0)>(raw0, taps0, v);
+        accumulate(v, p.in[0].weight);
+        resample_reduce<sig_mode(SIG, 1)>(raw1, taps1, v);
+        accumulate(v, p.in[1].weight);
+        if (NI == 3) {
+          resample_reduce<sig_mode(SIG, 2)>(raw2, taps2, v);
+          accumulate(v, p.in[2].weight);
+        }
       }
       apply_act4<ACT>(acc[0], acc[1]);
       apply_act4<ACT>(acc[2], acc[3]);
@@ -162,16 +191,25 @@ extern "C" int edet_fuse_dw(const edet_fuse_input* h_inputs, int n_inputs, const
   __half* ho = reinterpret_cast<__half*>(out);
   cudaStream_t s = as_stream(stream);
   cudaError_t err = cudaSuccess;
+  const int sig = fuse_signature(p);
+#define EDET_FUSE_DW(ACT)                                                                          \
+  switch (sig) {                                                                                   \
+    case kSigSameUp: err = launch_pdl(fuse_dw_kernel<ACT, kSigSameUp>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break; \
+    case kSigSameSameDown: err = launch_pdl(fuse_dw_kernel<ACT, kSigSameSameDown>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break; \
+    case kSigSameDown: err = launch_pdl(fuse_dw_kernel<ACT, kSigSameDown>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break; \
+    default: err = launch_pdl(fuse_dw_kernel<ACT, kSigGeneric>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break; \
+  }
   switch (act) {
-    case EDET_ACT_SWISH: err = launch_pdl(fuse_dw_kernel<EDET_ACT_SWISH>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break;
-    case EDET_ACT_RELU6: err = launch_pdl(fuse_dw_kernel<EDET_ACT_RELU6>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break;
-    case EDET_ACT_RELU: err = launch_pdl(fuse_dw_kernel<EDET_ACT_RELU>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break;
-    case EDET_ACT_HSWISH: err = launch_pdl(fuse_dw_kernel<EDET_ACT_HSWISH>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break;
-    case EDET_ACT_NONE: err = launch_pdl(fuse_dw_kernel<EDET_ACT_NONE>, grid, dim3(kFuseThreads), 0, s, p, hw, ho, h, wd, c, chunks); break;
+    case EDET_ACT_SWISH: EDET_FUSE_DW(EDET_ACT_SWISH); break;
+    case EDET_ACT_RELU6: EDET_FUSE_DW(EDET_ACT_RELU6); break;
+    case EDET_ACT_RELU: EDET_FUSE_DW(EDET_ACT_RELU); break;
+    case EDET_ACT_HSWISH: EDET_FUSE_DW(EDET_ACT_HSWISH); break;
+    case EDET_ACT_NONE: EDET_FUSE_DW(EDET_ACT_NONE); break;
     default:
       set_error("fuse_dw: bad activation %d", act);
       return EDET_ERR_INVALID;
   }
+#undef EDET_FUSE_DW
   EDET_CHECK_CUDA(err);
   return EDET_OK;
 }

@@ -502,13 +502,6 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   // k-block / smem row pitch: 16 halves (32B swizzle) for K <= 16, 32 (64B) for K <= 32, else
   // 64 (128B) -- unless two 64-wide stages of this (wide) N tile would not fit next to the store
   // slabs, in which case the narrower 32-wide stages keep the pipeline >= 3 deep.
-  p.block_k = k <= 16 ? 16 : (k <= 32 ? 32 : 64);
-  if (p.block_k == 64 && 2 * (BLOCK_M + p.block_n) * 128 + 40 * 1024 > kSmemLimit) p.block_k = 32;
-  p.desc_layout = p.block_k == 64 ? 2 : (p.block_k == 32 ? 4 : 6);
-  p.desc_sbo = 8 * p.block_k * 2;
-  p.num_k_blocks = ceil_div(k, p.block_k);
-  p.a_stage_bytes = BLOCK_M * p.block_k * 2;
-  p.b_stage_bytes = ((p.block_n * p.block_k * 2 + 1023) / 1024) * 1024;
   p.wbatch = wbatch;
   p.ldr = ldr;
   p.bias = bias;
@@ -521,17 +514,35 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   p.sched = next_sched_slot();
   if (!p.sched) return EDET_ERR_CUDA;
 
-  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
-  // thin stages (small K) leave room for a second store slab per epilogue warp
-  p.slabs_per_warp = stage_bytes <= 16 * 1024 ? 2 : 1;
-  if (teams == 3) p.slabs_per_warp = 2;
-  const int fixed = p.slabs_per_warp * epi_warps * slab_bytes + 2 * 256 * 4 +
-                    (2 * kMaxStages + 4 + 2 * kRing) * 8 + 16 + 4 * kRing;
-  int stages = (kSmemLimit - 1024 - fixed) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  EDET_CHECK_ARG(stages >= 2, "pointwise_tc: block_n %d leaves <2 pipeline stages", p.block_n);
-  p.num_stages = stages;
-  const int smem_bytes = 1024 + stages * stage_bytes + fixed;
+  // k-block / smem row pitch: 16 halves (32B swizzle) for K <= 16, 32 (64B) for K <= 32, else 64
+  // (128B).  Two store slabs per epilogue warp when they fit; a wide N tile falls back first to
+  // one slab, then to 32-wide k-blocks, so that the TMA ring stays >= 3 deep (>= 2 at worst).
+  const int ctrl = 2 * 256 * 4 + (2 * kMaxStages + 4 + 2 * kRing) * 8 + 16 + 4 * kRing;
+  int best_stages = 0, fixed = 0, stage_bytes = 0;
+  for (int attempt = 0; attempt < 4 && best_stages < 3; ++attempt) {
+    const int bk = k <= 16 ? 16 : (k <= 32 ? 32 : (attempt >= 2 ? 32 : 64));
+    const int slabs = (attempt & 1) ? 1 : 2;
+    const int a_bytes = BLOCK_M * bk * 2;
+    const int b_bytes = ((p.block_n * bk * 2 + 1023) / 1024) * 1024;
+    const int fx = slabs * epi_warps * slab_bytes + ctrl;
+    int st = (kSmemLimit - 1024 - fx) / (a_bytes + b_bytes);
+    if (st > kMaxStages) st = kMaxStages;
+    if (st > best_stages) {
+      best_stages = st;
+      p.block_k = bk;
+      p.slabs_per_warp = slabs;
+      p.a_stage_bytes = a_bytes;
+      p.b_stage_bytes = b_bytes;
+      fixed = fx;
+      stage_bytes = a_bytes + b_bytes;
+    }
+  }
+  EDET_CHECK_ARG(best_stages >= 2, "pointwise_tc: block_n %d leaves <2 pipeline stages", p.block_n);
+  p.num_stages = best_stages;
+  p.desc_layout = p.block_k == 64 ? 2 : (p.block_k == 32 ? 4 : 6);
+  p.desc_sbo = 8 * p.block_k * 2;
+  p.num_k_blocks = ceil_div(k, p.block_k);
+  const int smem_bytes = 1024 + best_stages * stage_bytes + fixed;
 
   CUtensorMap ma, mw, mo;
   int rc;

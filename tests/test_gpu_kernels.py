@@ -45,6 +45,13 @@ PW_CASES = [
     (2, 6400, 40, 64, utils.ACT_NONE, False, False),
     (1, 50000, 32, 16, utils.ACT_NONE, False, False),       # many tiles per CTA (pipeline wrap)
     (1, 3000, 320, 64, utils.ACT_RELU6, False, False),
+    # wide single-tile N with deep K (D3-D7x BiFPN / head widths): the shared-memory plan has to
+    # fall back to one store slab / 32-wide k-blocks
+    (1, 1000, 160, 160, utils.ACT_SWISH, False, False),
+    (2, 700, 224, 224, utils.ACT_NONE, False, False),
+    (1, 513, 256, 256, utils.ACT_SWISH, True, False),
+    (1, 900, 384, 384, utils.ACT_NONE, False, False),        # N > 256: tiles of 96 columns
+    (1, 260, 1344, 224, utils.ACT_NONE, True, True),        # D4-sized project
 ]
 
 
@@ -328,6 +335,44 @@ def test_fuse_dw_all_modes():
     fused = fused * torch.sigmoid(fused)
     ref = eo.depthwise_conv2d_same(fused, dwk.double().unsqueeze(-1)).permute(0, 2, 3, 1)
     assert torch.allclose(out.cpu().double(), ref, rtol=2e-3, atol=2e-3), (h, w)
+
+
+@pytest.mark.parametrize('sig', ['same_up', 'same_same_down', 'same_down'])
+@pytest.mark.parametrize('hw', [(20, 20), (13, 9), (40, 24), (5, 5)])
+def test_fuse_dw_bifpn_signatures(sig, hw):
+  """The three node shapes of a BiFPN cell run specialised instantiations (all input loads
+  issued up front; padded max-pool cells replaced by a clamped in-window tap): same results as
+  the oracle's resample / fuse / swish / depthwise on odd and even sizes."""
+  ops = _ops()
+  n, c = 2, 64
+  h, w = hw
+  g = torch.Generator().manual_seed(h * 31 + w + len(sig))
+  uh, uw = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+  dh, dw = h * 2 - (h % 2), w * 2 - (w % 2)
+  mk = lambda hh, ww: torch.randn(n, hh, ww, c, generator=g).half()
+  nchw = lambda t: t.double().permute(0, 3, 1, 2)
+  if sig == 'same_up':
+    tens = [mk(h, w), mk(uh, uw)]
+    modes = [(ops.RS_SAME, None), (ops.RS_UP, None)]
+    res = [nchw(tens[0]), eo.resize_nearest_tf1(nchw(tens[1]), h, w)]
+  elif sig == 'same_same_down':
+    tens = [mk(h, w), mk(h, w), mk(dh, dw)]
+    modes = [(ops.RS_SAME, None), (ops.RS_SAME, None), (ops.RS_DOWN, (3, 3, 2, 2))]
+    res = [nchw(tens[0]), nchw(tens[1]), eo.max_pool_same(nchw(tens[2]), (3, 3), (2, 2))]
+  else:
+    tens = [mk(h, w), mk(dh, dw)]
+    modes = [(ops.RS_SAME, None), (ops.RS_DOWN, (3, 3, 2, 2))]
+    res = [nchw(tens[0]), eo.max_pool_same(nchw(tens[1]), (3, 3), (2, 2))]
+  wts = [0.45, 0.35, 0.2][:len(tens)]
+  dwk = (torch.randn(3, 3, c, generator=g) / 3).half()
+  out = torch.empty(n, h, w, c, dtype=torch.float16, device=DEV)
+  specs = [(t.to(DEV), m, pool, wt) for t, (m, pool), wt in zip(tens, modes, wts)]
+  ops.fuse_dw(specs, dwk.reshape(9, c).to(DEV), out, utils.ACT_SWISH)
+  torch.cuda.synchronize()
+  fused = sum(r * np.float32(wt) for r, wt in zip(res, wts))
+  fused = fused * torch.sigmoid(fused)
+  ref = eo.depthwise_conv2d_same(fused, dwk.double().unsqueeze(-1)).permute(0, 2, 3, 1)
+  assert torch.allclose(out.cpu().double(), ref, rtol=2e-3, atol=2e-3), (sig, hw)
 
 
 CONV_CASES = [
