@@ -17,6 +17,8 @@ void set_error(const char* fmt, ...) {
 
 static std::atomic<int> g_opt_dw_impl{0};
 int option_dw_impl() { return g_opt_dw_impl.load(std::memory_order_relaxed); }
+static std::atomic<int> g_opt_stem_impl{0};
+int option_stem_impl() { return g_opt_stem_impl.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_pw_teams{0};
 int option_pw_teams() { return g_opt_pw_teams.load(std::memory_order_relaxed); }
 
@@ -78,6 +80,11 @@ extern "C" int edet_set_option(const char* name, int value) {
     g_opt_dw_impl.store(value);
     return EDET_OK;
   }
+  if (strcmp(name, "stem_impl") == 0) {
+    EDET_CHECK_ARG(value == 0 || value == 1, "set_option: stem_impl must be 0 or 1");
+    g_opt_stem_impl.store(value);
+    return EDET_OK;
+  }
   if (strcmp(name, "pw_teams") == 0) {
     EDET_CHECK_ARG(value == 0 || value == 2 || value == 3, "set_option: pw_teams must be 0, 2 or 3");
     g_opt_pw_teams.store(value);
@@ -91,6 +98,10 @@ extern "C" int edet_get_option(const char* name, int* value) {
   EDET_CHECK_ARG(name != nullptr && value != nullptr, "get_option: null pointer");
   if (strcmp(name, "dw_impl") == 0) {
     *value = option_dw_impl();
+    return EDET_OK;
+  }
+  if (strcmp(name, "stem_impl") == 0) {
+    *value = option_stem_impl();
     return EDET_OK;
   }
   if (strcmp(name, "pw_teams") == 0) {

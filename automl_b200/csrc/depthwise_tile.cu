@@ -11,12 +11,13 @@
 // warps of a CTA tile a (TR*WY) x (TC*WX) output tile.  HBM sees each input byte once per tile
 // (plus the halo, served by L2) and each output byte once.
 //
-// Persistent CTAs (two per SM) walk the work units (image, tile, 64-channel slice) round robin;
-// the channel slice varies fastest so that concurrently running CTAs touch the same DRAM pages.
+// Persistent CTAs (two per SM) take the work units (image, tile, 64-channel slice) from a global
+// counter; the channel slice varies fastest so that concurrently running CTAs touch the same DRAM
+// pages.
 //
 // Algorithmic HBM bytes per launch: 2*n*c*(h*w + ho*wo) + 2*k*k*c (+ 8*n*c of
-// int64 atomics for the SE squeeze).  Used for c >= 64 and maps of at least 24 x 24 outputs; the
-// register-tiled kernel of depthwise.cu keeps the small maps.
+// int64 atomics for the SE squeeze).  Used for c >= 64 when the fixed output tile covers the map
+// with <= 30 % waste (see eligible()); the register-tiled kernel of depthwise.cu keeps the rest.
 #include "tc_common.cuh"
 
 namespace edet {
@@ -252,11 +253,24 @@ static int launch_kernel(const CUtensorMap& mx, const Params& p, int grid, int a
   return EDET_ERR_UNSUPPORTED;
 }
 
-// True when the tiled kernel takes this shape (otherwise the register-tiled kernel runs).
+// True when the tiled kernel takes this shape (otherwise the register-tiled kernel runs): at least
+// one full 64-channel slice, and the fixed output tile of this (k, stride) must cover the map
+// without wasting more than ~30 % of its threads on out-of-map outputs (measured: 24 x 24 maps
+// under 16 x 16 tiles lose to the register kernel, 40 x 40 maps under 8 x 16 tiles win).
+template <int K, int S>
+static bool fits(int ho, int wo) {
+  using C = Cfg<K, S>;
+  const long long covered = static_cast<long long>(ceil_div(ho, C::TOH)) * C::TOH *
+                            static_cast<long long>(ceil_div(wo, C::TOW)) * C::TOW;
+  return static_cast<long long>(ho) * wo * 10 >= covered * 7;
+}
 bool eligible(int h, int wd, int c, int k, int stride) {
   const int ho = ceil_div(h, stride), wo = ceil_div(wd, stride);
-  (void)k;
-  return c >= kCB && ho >= 24 && wo >= 24;
+  if (c < kCB) return false;
+  if (k == 3 && stride == 1) return fits<3, 1>(ho, wo);
+  if (k == 3 && stride == 2) return fits<3, 2>(ho, wo);
+  if (k == 5 && stride == 1) return fits<5, 1>(ho, wo);
+  return fits<5, 2>(ho, wo);
 }
 
 template <int K, int S>

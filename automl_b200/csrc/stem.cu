@@ -99,6 +99,11 @@ stem_kernel(const float* __restrict__ in, __half* __restrict__ out, const __half
   }
 }
 
+namespace stemtc {   // stem_tc.cu
+bool eligible(int cout);
+int run(const float* in, __half* out, const __half* w, const float* bias, int n, int h, int wd,
+        int cout, int act, cudaStream_t stream);
+}  // namespace stemtc
 }  // namespace edet
 
 extern "C" int edet_stem_conv(const float* in, edet_half* out, const edet_half* w,
@@ -111,6 +116,10 @@ extern "C" int edet_stem_conv(const float* in, edet_half* out, const edet_half* 
   const __half* hw = reinterpret_cast<const __half*>(w);
   __half* ho_p = reinterpret_cast<__half*>(out);
   cudaStream_t s = as_stream(stream);
+  // default: implicit GEMM on the tensor cores (stem_tc.cu); "stem_impl" = 1 keeps this kernel
+  if (option_stem_impl() != 1 && stemtc::eligible(cout) &&
+      (act == EDET_ACT_SWISH || act == EDET_ACT_RELU6 || act == EDET_ACT_NONE))
+    return stemtc::run(in, ho_p, hw, bias, n, h, wd, cout, act, s);
   const int ho = ceil_div(h, 2), wo = ceil_div(wd, 2);
   const int pad_t = same_pad_before(h, 3, 2), pad_l = same_pad_before(wd, 3, 2);
   // ~8 pixel pairs per thread: staging the weights is amortised, yet there are enough CTAs

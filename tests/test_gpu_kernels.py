@@ -293,20 +293,31 @@ def test_se_fc(shape):
   assert torch.allclose(wt_scaled.cpu().double(), ref_w, rtol=1e-3, atol=1e-4)
 
 
-@pytest.mark.parametrize('hw,cout', [((64, 64), 32), ((33, 47), 48), ((8, 8), 64)])
-def test_stem_conv(hw, cout):
+@pytest.mark.parametrize('impl', ['tensor_core', 'cuda_core'])
+@pytest.mark.parametrize('hw,cout,n', [((64, 64), 32, 2), ((33, 47), 48, 2), ((8, 8), 64, 1),
+                                      ((127, 129), 40, 1), ((200, 96), 56, 3), ((5, 3), 24, 1)])
+def test_stem_conv(hw, cout, n, impl):
+  """Both stem kernels (implicit GEMM on tcgen05 with the float32 input split into fp16 hi + lo;
+  CUDA-core FFMA2) against the float64 oracle: even / odd sizes (asymmetric 'SAME' padding),
+  widths that are not multiples of 16 (N padding), several tiles per CTA."""
   ops = _ops()
   h, w = hw
-  g = torch.Generator().manual_seed(3)
-  x = torch.randn(2, h, w, 3, generator=g)
+  g = torch.Generator().manual_seed(3 + h + cout)
+  x = torch.randn(n, h, w, 3, generator=g) * 1.7
   k = (torch.randn(3, 3, 3, cout, generator=g) * 0.3).half()
   bias = torch.randn(cout, generator=g) * 0.1
-  out = torch.empty(2, -(-h // 2), -(-w // 2), cout, dtype=torch.float16, device=DEV)
-  ops.stem_conv(x.to(DEV), out, k.reshape(27, cout).to(DEV), bias.to(DEV), utils.ACT_SWISH)
-  torch.cuda.synchronize()
+  out = torch.empty(n, -(-h // 2), -(-w // 2), cout, dtype=torch.float16, device=DEV)
+  try:
+    ops.set_option('stem_impl', 0 if impl == 'tensor_core' else 1)
+    ops.stem_conv(x.to(DEV), out, k.reshape(27, cout).to(DEV), bias.to(DEV), utils.ACT_SWISH)
+    torch.cuda.synchronize()
+  finally:
+    ops.set_option('stem_impl', 0)
   ref = eo.conv2d_same(x.double().permute(0, 3, 1, 2), k.double(), stride=2) + bias.double().view(1, -1, 1, 1)
   ref = (ref * torch.sigmoid(ref)).permute(0, 2, 3, 1)
-  assert torch.allclose(out.cpu().double(), ref, rtol=2e-3, atol=2e-3)
+  got = out.cpu().double()
+  assert torch.allclose(got, ref, rtol=2e-3, atol=2e-3), float((got - ref).abs().max())
+  assert rel_l2(got, ref) < 4e-4          # one fp16 output rounding; the input keeps ~22 bits
 
 
 # ---------------------------------------------------------------------------------------------
