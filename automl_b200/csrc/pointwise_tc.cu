@@ -40,6 +40,7 @@ struct Epi {
 constexpr int kStoreCols = 64;
 constexpr int kMaxStages = 8;
 constexpr int kRing = 4;          // tile-index ring entries (power of two)
+constexpr int kMaxAccum = 4;      // TMEM accumulator stages (thin N tiles)
 constexpr int kSmemLimit = 113 * 1024;                    // two CTAs per SM share the 227 KiB
 
 struct Params {
@@ -50,7 +51,7 @@ struct Params {
   int desc_sbo;       // byte distance between 8-row groups in smem (8 * row pitch)
   int desc_layout;    // UMMA layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
   int slabs_per_warp; // private TMA-store staging slabs per epilogue warp (1 or 2)
-  int accum_stages;   // TMEM accumulator stages (2 when 2*block_n <= 256 columns, else 1)
+  int accum_stages;   // TMEM accumulator stages: 1..kMaxAccum, accum_stages * block_n <= 256 columns
   int wbatch, ldr, tmem_cols;
   int total_tiles;
   const float* bias;
@@ -88,13 +89,13 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + 2 * 256);
   uint64_t* full_bar = bars;                       // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]
-  uint64_t* tmem_full_bar = bars + 2 * kMaxStages;     // [2]
-  uint64_t* tmem_empty_bar = bars + 2 * kMaxStages + 2;  // [2]
+  uint64_t* tmem_full_bar = bars + 2 * kMaxStages;                 // [kMaxAccum]
+  uint64_t* tmem_empty_bar = bars + 2 * kMaxStages + kMaxAccum;    // [kMaxAccum]
   // Tile indices travel from the producer to the MMA warp and the epilogue warps through a small
   // ring: CTA i owns tile i, every further tile comes from a global counter (sched_next_tile), so
   // a CTA that gets its SM late -- another stream's kernel, e.g. the NMS of the previous batch,
   // was holding it -- simply finds less work instead of owning a full static share.
-  uint64_t* ring_full = bars + 2 * kMaxStages + 4;       // [kRing] producer -> consumers
+  uint64_t* ring_full = bars + 2 * kMaxStages + 2 * kMaxAccum;   // [kRing] producer -> consumers
   uint64_t* ring_empty = ring_full + kRing;              // [kRing] consumers -> producer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring_empty + kRing);
   volatile int* tile_ring = reinterpret_cast<volatile int*>(tmem_slot + 4);   // [kRing]
@@ -107,7 +108,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxAccum; ++s) {
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[s]), kEpiWarps);  // one arrive per epilogue warp
     }
@@ -193,8 +194,8 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       uint32_t phase = 0;
       for (int iter = 0;; ++iter) {
         if (ring_get(iter, false) >= p.total_tiles) break;
-        const int as = p.accum_stages == 2 ? (iter & 1) : 0;
-        const uint32_t aphase = p.accum_stages == 2 ? ((iter >> 1) & 1) : (iter & 1);
+        const int as = iter % p.accum_stages;
+        const uint32_t aphase = static_cast<uint32_t>(iter / p.accum_stages) & 1u;
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * p.block_n);
@@ -237,8 +238,8 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       const int t = ring_get(iter, true);
       if (t >= p.total_tiles) break;
       const TileCoord tc = decode_tile(t, p);
-      const int as = p.accum_stages == 2 ? (iter & 1) : 0;
-      const uint32_t aphase = p.accum_stages == 2 ? ((iter >> 1) & 1) : (iter & 1);
+      const int as = iter % p.accum_stages;
+      const uint32_t aphase = static_cast<uint32_t>(iter / p.accum_stages) & 1u;
       const int n0 = tc.n_blk * p.block_n;
       const int row = tc.m_blk * BLOCK_M + row_in_tile;
       const bool row_ok = row < p.rows;
@@ -348,8 +349,8 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
         const int t = ring_get(iter, true);
         if (t >= p.total_tiles) break;
         const TileCoord tc = decode_tile(t, p);
-        const int as = p.accum_stages == 2 ? (iter & 1) : 0;
-        const uint32_t aphase = p.accum_stages == 2 ? ((iter >> 1) & 1) : (iter & 1);
+        const int as = iter % p.accum_stages;
+        const uint32_t aphase = static_cast<uint32_t>(iter / p.accum_stages) & 1u;
         const int n0 = tc.n_blk * p.block_n;
         const int row = tc.m_blk * BLOCK_M + row_in_tile;
         const bool row_ok = row < p.rows;
@@ -361,14 +362,18 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
         tc_fence_after();
         const int n_valid = min(p.block_n, ((p.nout - n0 + 15) >> 4) << 4);
         const int num_units = (n_valid + 31) >> 5;
+        // unit u of tile `iter` belongs to team (u + iter) % TEAMS: thin layers (one or two units
+        // per tile) keep all three teams busy on consecutive tiles (up to kMaxAccum accumulators
+        // in flight) instead of leaving two of them idle
+        const int u_first = (team + TEAMS - iter % TEAMS) % TEAMS;
         int my_last = -1;
-        for (int u = team; u < num_units; u += TEAMS) my_last = u;
+        for (int u = u_first; u < num_units; u += TEAMS) my_last = u;
         if (my_last < 0) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
         }
-        for (int u = team; u < num_units; u += TEAMS) {
+        for (int u = u_first; u < num_units; u += TEAMS) {
           const int cols = min(32, n_valid - u * 32);      // 16 or 32
           uint8_t* my_stage = my_slabs + (p.slabs_per_warp == 2 ? (store_cnt & 1) * kSlabBytes : 0);
           ++store_cnt;
@@ -506,7 +511,11 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   p.ldr = ldr;
   p.bias = bias;
   p.residual = residual;
-  p.accum_stages = (2 * p.block_n <= 256) ? 2 : 1;
+  // accumulator stages: as many as fit in this CTA's 256 TMEM columns (two CTAs per SM), up to 4
+  // with three teams (so that every team can work on its own tile of a thin layer), 2 with two
+  p.accum_stages = 256 / p.block_n;
+  if (p.accum_stages < 1) p.accum_stages = 1;
+  if (p.accum_stages > (teams == 3 ? kMaxAccum : 2)) p.accum_stages = teams == 3 ? kMaxAccum : 2;
   int cols = 32;
   while (cols < p.accum_stages * p.block_n) cols *= 2;
   p.tmem_cols = cols;
@@ -517,7 +526,7 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   // k-block / smem row pitch: 16 halves (32B swizzle) for K <= 16, 32 (64B) for K <= 32, else 64
   // (128B).  Two store slabs per epilogue warp when they fit; a wide N tile falls back first to
   // one slab, then to 32-wide k-blocks, so that the TMA ring stays >= 3 deep (>= 2 at worst).
-  const int ctrl = 2 * 256 * 4 + (2 * kMaxStages + 4 + 2 * kRing) * 8 + 16 + 4 * kRing;
+  const int ctrl = 2 * 256 * 4 + (2 * kMaxStages + 2 * kMaxAccum + 2 * kRing) * 8 + 16 + 4 * kRing;
   int best_stages = 0, fixed = 0, stage_bytes = 0;
   for (int attempt = 0; attempt < 4 && best_stages < 3; ++attempt) {
     const int bk = k <= 16 ? 16 : (k <= 32 ? 32 : (attempt >= 2 ? 32 : 64));

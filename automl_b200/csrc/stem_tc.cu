@@ -11,9 +11,10 @@
 // tile (27 loads + 27 splits per pixel) and run the epilogue.
 //
 // One CTA (128 threads, one thread per output pixel of the tile) per tile, persistent with the
-// dynamic tile scheduler, up to 6 CTAs per SM:
-//   1. all threads: the (17 x 33 x 3) float32 input patch -> shared memory, coalesced, zero filled
-//      outside the image ('SAME' padding)
+// dynamic tile scheduler, 5 CTAs per SM:
+//   1. all threads: the (17 x 33 x 3) float32 input patch -> shared memory with cp.async (coalesced,
+//      zero filled outside the image = 'SAME' padding), double buffered: the NEXT tile's patch is
+//      in flight while this tile is converted, multiplied and written out
 //   2. thread m: its 27 inputs -> hi / lo halves -> row m of the swizzled A tile
 //   3. one thread: 4 x tcgen05.mma (M 128, N cout rounded to 16, K 16)
 //   4. warp w: TMEM lanes 32w.. -> + bias -> activation -> fp16 -> global
@@ -30,6 +31,7 @@ constexpr int TH = 8, TW = 16;                       // output tile: 128 pixels 
 constexpr int IH = 2 * TH + 1, IW = 2 * TW + 1;      // input patch (stride 2, 3 x 3 window)
 constexpr int kRowFloats = IW * 3;                   // 99 floats per patch row
 constexpr int kInFloats = IH * kRowFloats;           // 1683
+constexpr int kInPad = (kInFloats + 3) & ~3;         // floats per (double-buffered) patch slot
 constexpr int kABytes = 128 * 128;                   // [128 rows][64 halves]
 constexpr int kMaxN = 64;
 constexpr int kBBytes = kMaxN * 128;
@@ -39,9 +41,14 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+// 4-byte asynchronous global -> shared copy; src_bytes == 0 writes a zero (the 'SAME' padding)
+__device__ __forceinline__ void cp_async_f32(uint32_t dst, const float* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src),
+               "r"(valid ? 4 : 0)
+               : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 struct Params {
   const float* in;      // [n, h, w, 3]
@@ -62,8 +69,8 @@ stem_tc_kernel(const Params p) {
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + kABytes;
-  float* in_s = reinterpret_cast<float*>(smem_b + kBBytes);                 // [IH][IW][3]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(in_s + ((kInFloats + 3) & ~3));
+  float* in_s = reinterpret_cast<float*>(smem_b + kBBytes);                 // [2][IH][IW][3]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(in_s + 2 * kInPad);
   const uint32_t mma_bar = smem_u32(bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
   volatile int* next_tile_s = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [2]
@@ -105,7 +112,31 @@ stem_tc_kernel(const Params p) {
   const int mr = m / TW, mc = m % TW;
   const int row_floats = p.w * 3;
 
+  // The input patch of the NEXT tile is fetched with cp.async (4-byte copies, zero fill outside the
+  // image) into the other half of a double buffer while the current tile is converted, multiplied
+  // and written out, so its global-memory latency is off the critical path.
+  auto fetch_patch = [&](int tile, int slot) {
+    const int tx_i = tile % p.tiles_x;
+    const int ty_i = (tile / p.tiles_x) % p.tiles_y;
+    const int n = tile / (p.tiles_x * p.tiles_y);
+    const int iy0 = ty_i * TH * 2 - p.pad_t;
+    const int xf0 = (tx_i * TW * 2 - p.pad_l) * 3;     // first float of the patch inside an image row
+    const float* img = p.in + static_cast<size_t>(n) * p.h * row_floats;
+    const uint32_t dst = in_u32 + slot * kInPad * 4;
+    int r = 0, cf = threadIdx.x;                      // kThreads (128) = kRowFloats (99) + 29
+    if (cf >= kRowFloats) { cf -= kRowFloats; r = 1; }
+    for (int i = threadIdx.x; i < kInFloats; i += kThreads) {
+      const int iy = iy0 + r, xf = xf0 + cf;
+      const bool ok = iy >= 0 && iy < p.h && xf >= 0 && xf < row_floats;
+      cp_async_f32(dst + i * 4, ok ? img + static_cast<size_t>(iy) * row_floats + xf : p.in, ok);
+      r += 1; cf += kThreads - kRowFloats;
+      if (cf >= kRowFloats) { cf -= kRowFloats; r += 1; }
+    }
+    cp_async_commit();
+  };
+
   int t = blockIdx.x;
+  if (t < p.total_tiles) fetch_patch(t, 0);
   for (int it = 0; t < p.total_tiles; ++it) {
     if (threadIdx.x == 0) next_tile_s[it & 1] = sched_next_tile(p.sched, p.total_tiles);
     const int tx_i = t % p.tiles_x;
@@ -113,24 +144,15 @@ stem_tc_kernel(const Params p) {
     const int n = t / (p.tiles_x * p.tiles_y);
     const int y0 = ty_i * TH, x0 = tx_i * TW;
 
-    // ---- 1. input patch -> shared memory (coalesced rows of 99 floats, zero outside) ---------
-    {
-      const int iy0 = y0 * 2 - p.pad_t;
-      const int xf0 = (x0 * 2 - p.pad_l) * 3;        // first float of the patch inside an image row
-      const float* img = p.in + static_cast<size_t>(n) * p.h * row_floats;
-      for (int i = threadIdx.x; i < kInFloats; i += kThreads) {
-        const int r = i / kRowFloats, cf = i - r * kRowFloats;
-        const int iy = iy0 + r, xf = xf0 + cf;
-        float v = 0.f;
-        if (iy >= 0 && iy < p.h && xf >= 0 && xf < row_floats)
-          v = __ldg(img + static_cast<size_t>(iy) * row_floats + xf);
-        sts_f32(in_u32 + i * 4, v);
-      }
-    }
-    __syncthreads();
+    // ---- 1. this tile's patch has landed; start fetching the next tile's ------------------------
+    cp_async_wait_all();
+    __syncthreads();                                   // patch + next_tile_s visible to everyone
+    const int t_next = next_tile_s[it & 1];
+    if (t_next < p.total_tiles) fetch_patch(t_next, (it + 1) & 1);
+    const uint32_t patch_u32 = in_u32 + (it & 1) * kInPad * 4;
     // ---- 2. A row m: 27 hi halves, 27 lo halves, 10 zeros -> 8 swizzled 16-byte pieces ----------
     {
-      const uint32_t src = in_u32 + (2 * mr * IW + 2 * mc) * 3 * 4;
+      const uint32_t src = patch_u32 + (2 * mr * IW + 2 * mc) * 3 * 4;
       __half hv[64];
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
@@ -205,7 +227,7 @@ stem_tc_kernel(const Params p) {
     tc_fence_before();
     __syncthreads();       // TMEM, A and the input patch are free for the next tile
     tc_fence_after();
-    t = next_tile_s[it & 1];
+    t = t_next;
   }
 
   tc_fence_before();
@@ -249,8 +271,9 @@ int run(const float* in, __half* out, const __half* w, const float* bias, int n,
   if (!p.sched) return EDET_ERR_CUDA;
   const int sms = device_sm_count();
   if (!sms) return EDET_ERR_CUDA;
-  const int smem_bytes = 1024 + kABytes + kBBytes + ((kInFloats + 3) & ~3) * 4 + 64;
-  int per_sm = 6;
+  const int smem_bytes = 1024 + kABytes + kBBytes + 2 * kInPad * 4 + 64;
+  int per_sm = 232448 / (smem_bytes + 1024);
+  if (per_sm > 6) per_sm = 6;
   if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;
   const int grid = p.total_tiles < per_sm * sms ? p.total_tiles : per_sm * sms;
   if (act == EDET_ACT_SWISH) return launch<EDET_ACT_SWISH>(p, grid, smem_bytes, stream);
