@@ -19,6 +19,8 @@ static std::atomic<int> g_opt_dw_impl{0};
 int option_dw_impl() { return g_opt_dw_impl.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_stem_impl{0};
 int option_stem_impl() { return g_opt_stem_impl.load(std::memory_order_relaxed); }
+static std::atomic<int> g_opt_sepconv_impl{0};
+int option_sepconv_impl() { return g_opt_sepconv_impl.load(std::memory_order_relaxed); }
 static std::atomic<int> g_opt_pw_teams{0};
 int option_pw_teams() { return g_opt_pw_teams.load(std::memory_order_relaxed); }
 
@@ -80,6 +82,11 @@ extern "C" int edet_set_option(const char* name, int value) {
     g_opt_dw_impl.store(value);
     return EDET_OK;
   }
+  if (strcmp(name, "sepconv_impl") == 0) {
+    EDET_CHECK_ARG(value == 0 || value == 1, "set_option: sepconv_impl must be 0 or 1");
+    g_opt_sepconv_impl.store(value);
+    return EDET_OK;
+  }
   if (strcmp(name, "stem_impl") == 0) {
     EDET_CHECK_ARG(value == 0 || value == 1, "set_option: stem_impl must be 0 or 1");
     g_opt_stem_impl.store(value);
@@ -98,6 +105,10 @@ extern "C" int edet_get_option(const char* name, int* value) {
   EDET_CHECK_ARG(name != nullptr && value != nullptr, "get_option: null pointer");
   if (strcmp(name, "dw_impl") == 0) {
     *value = option_dw_impl();
+    return EDET_OK;
+  }
+  if (strcmp(name, "sepconv_impl") == 0) {
+    *value = option_sepconv_impl();
     return EDET_OK;
   }
   if (strcmp(name, "stem_impl") == 0) {

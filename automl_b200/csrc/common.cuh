@@ -174,6 +174,7 @@ inline cudaStream_t as_stream(edet_stream_t s) { return reinterpret_cast<cudaStr
 // Library options (edet_set_option): implementation switches for A/B measurements.
 int option_dw_impl();   // 0 auto (tiled kernel where eligible), 1 register kernel only, 2 = 0
 int option_stem_impl(); // 0 auto (tensor-core stem), 1 CUDA-core stem kernel
+int option_sepconv_impl();  // 0 auto (TMA-staged input for c <= 64), 1 loads straight from global
 int option_pw_teams();  // 0 auto, 2 / 3 = force that many epilogue teams in pointwise_tc
 constexpr int kMaxDevices = 64;
 int current_device();                 // ordinal of the current device, -1 (+ error text) on failure

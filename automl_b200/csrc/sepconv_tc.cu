@@ -476,6 +476,225 @@ sepconv_direct_kernel(const __grid_constant__ CUtensorMap map_w, const Params p)
   }
 }
 
+// ---- single-input form, c <= 64, input tile staged by TMA --------------------------------------
+// Same arithmetic and thread mapping as sepconv_direct_kernel, but the (8+2) x (16+2) x 64-channel
+// input tile is fetched by one bulk tensor copy (out-of-image pixels arrive as zeros = 'SAME'
+// padding, so there is no border path), double buffered: the NEXT tile's copy is issued as soon as
+// its index is known and overlaps this tile's depthwise, MMA and epilogue.  The depthwise reads
+// come from shared memory (128 contiguous bytes per warp and pixel, conflict free).
+constexpr int kInTileBytes = HT * WT * 128;
+
+template <int ACT_POST>
+__global__ void __launch_bounds__(kDirectThreads, 3)
+sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
+                          const __grid_constant__ CUtensorMap map_x, const Params p) {
+  pdl_launch_dependents();
+  constexpr int IN_ROWS = TH + 2, IN_COLS = 4 + 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;                                  // [128][64] halves, swizzled
+  uint8_t* smem_b = smem_a + kAtomBytesA;                  // [npad][64] halves, swizzled
+  uint8_t* smem_in = smem_b + p.b_atom_bytes;              // 2 x [HT][WT][64] halves, dense
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_in + 2 * kInTileBytes);
+  const uint32_t w_bar = smem_u32(bars);
+  const uint32_t mma_bar = smem_u32(bars + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  volatile int* next_tile_s = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(w_bar, 1);
+    mbar_init(mma_bar, 1);
+    mbar_init(smem_u32(bars + 2), 1);
+    mbar_init(smem_u32(bars + 3), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(static_cast<uint32_t>(p.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // the K-padding channels of A multiply TMA-zero-filled weights: they must be finite -> zero A once
+  for (int i = threadIdx.x; i < kAtomBytesA / 16; i += kDirectThreads)
+    reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0u, 0u, 0u, 0u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(w_bar, static_cast<uint32_t>(p.npad * 128));
+    tma_load_3d(smem_u32(smem_b), &map_w, w_bar, 0, 0, 0);
+  }
+  const int c = p.c, h = p.h, wd = p.w;
+  const int cp_count = c >> 1;
+  const int items = 4 * cp_count;   // (4-column group, channel pair)
+  const __half2* w2 = reinterpret_cast<const __half2*>(p.dw_w);
+  pdl_wait_prior();
+
+  auto fetch_tile = [&](int tile, int slot) {          // thread 0 only
+    const int tx_i = tile % p.tiles_x;
+    const int ty_i = (tile / p.tiles_x) % p.tiles_y;
+    const int n = tile / (p.tiles_x * p.tiles_y);
+    const uint32_t bar = smem_u32(bars + 2 + slot);
+    mbar_expect_tx(bar, static_cast<uint32_t>(kInTileBytes));
+    tma_load_4d(smem_u32(smem_in + slot * kInTileBytes), &map_x, bar, 0, tx_i * TW - 1, ty_i * TH - 1, n);
+  };
+
+  const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(p.npad >> 3) << 17) |
+                         (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+  const uint32_t a_u32 = smem_u32(smem_a);
+  uint32_t mma_phase = 0;
+  bool weights_ready = false;
+
+  int t = blockIdx.x;
+  if (threadIdx.x == 0 && t < p.total_tiles) fetch_tile(t, 0);
+  for (int it = 0; t < p.total_tiles; ++it) {
+    if (threadIdx.x == 0) {
+      // slot (it + 1) & 1 was last read in iteration it - 1, which ended with a CTA barrier
+      const int tn = sched_next_tile(p.sched, p.total_tiles);
+      next_tile_s[it & 1] = tn;
+      if (tn < p.total_tiles) fetch_tile(tn, (it + 1) & 1);
+    }
+    const int tx_i = t % p.tiles_x;
+    const int ty_i = (t / p.tiles_x) % p.tiles_y;
+    const int n = t / (p.tiles_x * p.tiles_y);
+    const int y0 = ty_i * TH, x0 = tx_i * TW;
+
+    // ---- depthwise 3x3 from the shared-memory tile -> A tile -----------------------------------
+    mbar_wait(smem_u32(bars + 2 + (it & 1)), static_cast<uint32_t>(it >> 1) & 1u);
+    const uint32_t in_u32 = smem_u32(smem_in + (it & 1) * kInTileBytes);
+    for (int e = threadIdx.x; e < items; e += kDirectThreads) {
+      const int xg = e / cp_count, cp = e - xg * cp_count;
+      float2 wreg[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) wreg[i] = __half22float2(__ldg(w2 + i * cp_count + cp));
+      float2 acc[TH][4];
+#pragma unroll
+      for (int r = 0; r < TH; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = make_float2(0.f, 0.f);
+      const uint32_t base = in_u32 + static_cast<uint32_t>((xg * 4) * 128 + cp * 4);
+#pragma unroll
+      for (int ir = 0; ir < IN_ROWS; ++ir) {
+        float2 xv[IN_COLS];
+#pragma unroll
+        for (int j = 0; j < IN_COLS; ++j) {
+          uint32_t raw;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(raw) : "r"(base + static_cast<uint32_t>((ir * WT + j) * 128)));
+          xv[j] = __half22float2(*reinterpret_cast<const __half2*>(&raw));
+        }
+#pragma unroll
+        for (int r = 0; r < TH; ++r) {
+          const int ky = ir - r;
+          if (ky >= 0 && ky < 3) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx)
+                acc[r][j] = __ffma2_rn(xv[j + kx], wreg[ky * 3 + kx], acc[r][j]);
+          }
+        }
+      }
+      // row = r * 16 + xg * 4 + j; 16-byte piece (cp >> 2), xor-swizzled
+      const uint32_t abase = a_u32 + (cp & 3) * 4;
+      const int piece = (cp >> 2) & 7;
+#pragma unroll
+      for (int r = 0; r < TH; ++r) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = r * TW + xg * 4 + j;
+          const __half2 hv = __floats2half2_rn(acc[r][j].x, acc[r][j].y);
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(abase + row * 128 + ((piece ^ (row & 7)) << 4)),
+                       "r"(*reinterpret_cast<const uint32_t*>(&hv))
+                       : "memory");
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- D = A * W^T ---------------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+      if (!weights_ready) {
+        mbar_wait(w_bar, 0);
+        weights_ready = true;
+      }
+      tc_fence_after();
+      const uint64_t da = make_smem_desc(a_u32, 1024, 2);
+      const uint64_t db = make_smem_desc(smem_u32(smem_b), 1024, 2);
+      const int ksteps = min(4, p.kpad >> 4);
+      for (int ks = 0; ks < ksteps; ++ks)
+        tc_mma_f16(tmem_base, da + static_cast<uint64_t>(ks * 2), db + static_cast<uint64_t>(ks * 2),
+                   idesc, ks > 0 ? 1u : 0u);
+      tc_commit(mma_bar);
+    }
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: warp w owns TMEM lanes (= tile rows) 32w .. 32w+31, all columns ---------------
+    {
+      const int row = warp * 32 + lane;
+      const int y = y0 + row / TW, x = x0 + row % TW;
+      const bool ok = y < h && x < wd;
+      __half* orow = p.out + ((static_cast<size_t>(n) * h + y) * wd + x) * p.ldo;
+      for (int col = 0; col < p.npad; col += 16) {
+        float v[16];
+        tc_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(col), v);
+        tc_wait_ld();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cc = col + hh * 8;
+          if (ok && cc < p.nout) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cc));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cc + 4));
+            float2 r0 = __fadd2_rn(make_float2(v[hh * 8 + 0], v[hh * 8 + 1]), make_float2(b0.x, b0.y));
+            float2 r1 = __fadd2_rn(make_float2(v[hh * 8 + 2], v[hh * 8 + 3]), make_float2(b0.z, b0.w));
+            float2 r2 = __fadd2_rn(make_float2(v[hh * 8 + 4], v[hh * 8 + 5]), make_float2(b1.x, b1.y));
+            float2 r3 = __fadd2_rn(make_float2(v[hh * 8 + 6], v[hh * 8 + 7]), make_float2(b1.z, b1.w));
+            if (ACT_POST != EDET_ACT_NONE) {
+              apply_act4<ACT_POST>(r0, r1);
+              apply_act4<ACT_POST>(r2, r3);
+            }
+            const float o[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};
+            *reinterpret_cast<uint4*>(orow + cc) = float_to_half8(o);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    t = next_tile_s[it & 1];
+  }
+
+  if (threadIdx.x == 0 && !weights_ready) mbar_wait(w_bar, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(p.tmem_cols))
+                 : "memory");
+  }
+}
+
+template <int POST>
+static int launch_direct_tma(const CUtensorMap& mw, const CUtensorMap& mx, const Params& p, int grid,
+                             int smem_bytes, cudaStream_t stream) {
+  auto kern = sepconv_direct_tma_kernel<POST>;
+  static int configured[kMaxDevices];
+  if (int rc = ensure_dynamic_smem(kern, smem_bytes, configured)) return rc;
+  EDET_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kDirectThreads), smem_bytes, stream, mw, mx, p));
+  return EDET_OK;
+}
+
 template <int POST>
 static int launch_direct(const CUtensorMap& mw, const Params& p, int grid, int smem_bytes,
                          cudaStream_t stream) {
@@ -544,6 +763,21 @@ extern "C" int edet_sepconv(const edet_fuse_input* h_inputs, int n_inputs, int p
   if (per_sm > cap) per_sm = cap;
   if (per_sm < 1) per_sm = 1;
   const int grid = p.total_tiles < per_sm * sm_count ? p.total_tiles : per_sm * sm_count;
+  if (direct && p.katoms == 1 && option_sepconv_impl() != 1) {
+    // c <= 64: the input tile comes through TMA, double buffered (sepconv_direct_tma_kernel)
+    CUtensorMap mx;
+    if (int rc = make_map4(&mx, p.fuse.in[0].ptr, c, wd, h, n, 64, WT, HT, /*swizzle=*/false)) return rc;
+    const int smem_tma = 1024 + kAtomBytesA + p.b_atom_bytes + 2 * kInTileBytes + 128;
+    int per = 232448 / (smem_tma + 1024);
+    if (per * p.tmem_cols > 512) per = 512 / p.tmem_cols;
+    if (per > 3) per = 3;
+    const int grid_tma = p.total_tiles < per * sm_count ? p.total_tiles : per * sm_count;
+    if (post_act == EDET_ACT_SWISH) return launch_direct_tma<EDET_ACT_SWISH>(mw, mx, p, grid_tma, smem_tma, s);
+    if (post_act == EDET_ACT_RELU6) return launch_direct_tma<EDET_ACT_RELU6>(mw, mx, p, grid_tma, smem_tma, s);
+    if (post_act == EDET_ACT_NONE) return launch_direct_tma<EDET_ACT_NONE>(mw, mx, p, grid_tma, smem_tma, s);
+    set_error("sepconv: unsupported activation %d", post_act);
+    return EDET_ERR_UNSUPPORTED;
+  }
   if (direct) {
     if (post_act == EDET_ACT_SWISH) return launch_direct<EDET_ACT_SWISH>(mw, p, grid, smem_bytes, s);
     if (post_act == EDET_ACT_RELU6) return launch_direct<EDET_ACT_RELU6>(mw, p, grid, smem_bytes, s);

@@ -59,7 +59,8 @@ const char* edet_last_error(void);
 /* Process-wide implementation switches, for A/B measurements and tests only (results are the same
  * for every setting).  Options: "dw_impl" = 0 (default: TMA-tiled depthwise kernel where eligible,
  * register-tiled kernel otherwise) | 1 (register-tiled kernel only); "pw_teams" = 0 (default:
- * three epilogue teams) | 2 | 3; "stem_impl" = 0 (default: tensor-core stem) | 1 (CUDA-core stem). */
+ * three epilogue teams) | 2 | 3; "stem_impl" = 0 (default: tensor-core stem) | 1 (CUDA-core stem);
+ * "sepconv_impl" = 0 (default: TMA-staged input tile for c <= 64) | 1 (loads from global). */
 int edet_set_option(const char* name, int value);
 int edet_get_option(const char* name, int* value);
 /* Number of SMs / compute capability of the current device (major*10+minor). */

@@ -434,15 +434,23 @@ SEP_CASES = [
     (1, (40, 40), 64, 64, utils.ACT_NONE, utils.ACT_SWISH, ['same']),              # several tiles per CTA
     (1, (9, 17), 112, 112, utils.ACT_RELU6, utils.ACT_NONE, ['same', 'down']),
     (3, (80, 80), 64, 64, utils.ACT_NONE, utils.ACT_SWISH, ['same']),              # persistent loop
+    (2, (33, 47), 64, 64, utils.ACT_NONE, utils.ACT_SWISH, ['same']),              # ragged tiles (TMA zero fill)
+    (1, (17, 9), 48, 48, utils.ACT_NONE, utils.ACT_RELU6, ['same']),               # c < 64: box wider than the tensor
+    (2, (24, 24), 64, 40, utils.ACT_NONE, utils.ACT_NONE, ['same']),               # nout != c
 ]
 
 
+@pytest.mark.parametrize('impl', [0, 1])
 @pytest.mark.parametrize('case', SEP_CASES)
-def test_sepconv(case):
+def test_sepconv(case, impl):
   """edet_sepconv == edet_fuse_dw + edet_pointwise_conv bit for bit (same fp16 rounding of the
-  depthwise result), and both match the float64 restatement."""
+  depthwise result), and both match the float64 restatement.  impl 0 / 1: input tile of the
+  single-input form staged by TMA / loaded straight from global memory."""
   ops = _ops()
   n, (h, w), c, nout, pre, post, modes = case
+  if impl == 1 and len(modes) > 1:
+    pytest.skip('the option only affects the single-input form')
+  ops.set_option('sepconv_impl', impl)
   g = torch.Generator().manual_seed(31 + h + c)
   specs, ref_in = [], []
   wsum = float(len(modes))
@@ -468,6 +476,7 @@ def test_sepconv(case):
   ops.fuse_dw(specs, dw_w.to(DEV), tmp, pre)
   ops.pointwise_conv(tmp, pw.to(DEV), bias.to(DEV), two, post, rows=n * h * w, nout=nout)
   torch.cuda.synchronize()
+  ops.set_option('sepconv_impl', 0)
   assert torch.equal(out[..., :nout], two[..., :nout])
   assert bool((out[..., nout:] == 7.0).all())       # the padding columns are not touched
   # float64 restatement
