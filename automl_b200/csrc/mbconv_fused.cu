@@ -219,13 +219,80 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
     }
     tc_fence_before();   // the TMEM reads are ordered before the next tile's MMA by this barrier
     __syncthreads();
-    // ---- 4. depthwise over the smem E tile: one (output row, channel pair) per work item ----
+    // ---- 4. depthwise over the smem E tile ------------------------------------------------------
     {
       const int cpn = cv >> 1;
       const int oy0 = tl.ty * OTW, ox0 = tl.tx * OTW;
       const int rows = min(OTW, p.ho - oy0), cols = min(OTW, p.wo - ox0);
       const int cm2 = p.cmid >> 1;
       const uint32_t e_u32 = smem_u32(smem_e);
+      if constexpr (K == 3 && S == 2) {
+        // One work item = (pair of output columns, channel pair): the thread produces the whole
+        // 7-row column pair from registers (weights loaded once, every input pixel read once per
+        // thread: 15 x 5 ld.shared for 14 outputs), instead of one output row per item with the
+        // weights re-read per item -- the depthwise phase was 2/3 of this kernel's instructions.
+        constexpr int CG = 2;
+        constexpr int NCG = (OTW + CG - 1) / CG;
+        constexpr int IN_R = (OTW - 1) * S + K, IN_C = (CG - 1) * S + K;
+        for (int item = threadIdx.x; item < NCG * cpn; item += kThreads) {
+          const int xg = item / cpn, cp = item - xg * cpn;
+          const __half2* wd2 = reinterpret_cast<const __half2*>(p.wd) + ((cbase >> 1) + cp);
+          float2 wk[K * K];
+#pragma unroll
+          for (int i = 0; i < K * K; ++i) wk[i] = __half22float2(__ldg(wd2 + i * cm2));
+          uint32_t coff[IN_C];     // the last column group reads a clamped (discarded) column
+#pragma unroll
+          for (int j = 0; j < IN_C; ++j)
+            coff[j] = e_u32 + static_cast<uint32_t>(min(xg * CG * S + j, kPatch - 1) * kEPitch + cp * 4);
+          float2 acc[OTW][CG];
+#pragma unroll
+          for (int r = 0; r < OTW; ++r)
+#pragma unroll
+            for (int tx = 0; tx < CG; ++tx) acc[r][tx] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int ir = 0; ir < IN_R; ++ir) {
+            float2 xv[IN_C];
+#pragma unroll
+            for (int j = 0; j < IN_C; ++j) xv[j] = h2_bits_to_f2(lds_b32(coff[j] + ir * kPatch * kEPitch));
+#pragma unroll
+            for (int r = 0; r < OTW; ++r) {
+              const int ky = ir - r * S;
+              if (ky >= 0 && ky < K) {
+#pragma unroll
+                for (int tx = 0; tx < CG; ++tx)
+#pragma unroll
+                  for (int kx = 0; kx < K; ++kx)
+                    acc[r][tx] = __ffma2_rn(xv[tx * S + kx], wk[ky * K + kx], acc[r][tx]);
+              }
+            }
+          }
+          const float2 bd = __ldg(reinterpret_cast<const float2*>(p.bias_d + cbase) + cp);
+          __half2* ocol = reinterpret_cast<__half2*>(p.out) +
+                          ((static_cast<size_t>(tl.n) * p.ho + oy0) * p.wo + ox0 + xg * CG) * cm2 +
+                          (cbase >> 1) + cp;
+          float2 ssum = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int r = 0; r < OTW; ++r) {
+            float2 o0 = __fadd2_rn(acc[r][0], bd), o1 = __fadd2_rn(acc[r][1], bd);
+            apply_act4<ACT>(o0, o1);
+            if (r < rows) {
+              if (xg * CG < cols) {
+                if (HAS_SE) ssum = __fadd2_rn(ssum, o0);
+                ocol[static_cast<size_t>(r) * p.wo * cm2] = __floats2half2_rn(o0.x, o0.y);
+              }
+              if (xg * CG + 1 < cols) {
+                if (HAS_SE) ssum = __fadd2_rn(ssum, o1);
+                ocol[static_cast<size_t>(r) * p.wo * cm2 + cm2] = __floats2half2_rn(o1.x, o1.y);
+              }
+            }
+          }
+          if (HAS_SE) {
+            atomicAdd(&se_s[2 * cp], static_cast<unsigned long long>(__float2ll_rn(ssum.x * 1048576.f)));
+            atomicAdd(&se_s[2 * cp + 1], static_cast<unsigned long long>(__float2ll_rn(ssum.y * 1048576.f)));
+          }
+        }
+      } else {
+      // one (output row, channel pair) per work item
       for (int item = threadIdx.x; item < rows * cpn; item += kThreads) {
         const int oyl = item / cpn, cp = item - oyl * cpn;
         const __half2* wd2 = reinterpret_cast<const __half2*>(p.wd) + ((cbase >> 1) + cp);
@@ -269,6 +336,7 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
           atomicAdd(&se_s[2 * cp], static_cast<unsigned long long>(__float2ll_rn(ssum.x * 1048576.f)));
           atomicAdd(&se_s[2 * cp + 1], static_cast<unsigned long long>(__float2ll_rn(ssum.y * 1048576.f)));
         }
+      }
       }
       if (HAS_SE) {
         __syncthreads();
