@@ -57,7 +57,7 @@ class Engine(object):
   """One network instance bound to one device, one batch size and one image size."""
 
   def __init__(self, config, weights, batch_size, device='cuda:0', pw_impl=ops.PW_TCGEN05,
-               use_cuda_graph=True, image_id_base=0, fuse_mbconv_front=True,
+               use_cuda_graph=True, image_id_base=0, fuse_mbconv_front=False,
                fuse_sepconv=True, fuse_sepconv_nodes=False):
     if not torch.cuda.is_available():
       raise RuntimeError('automl_b200.Engine needs a CUDA device; there is no CPU fallback')
@@ -163,9 +163,12 @@ class Engine(object):
       h, wd = cur_hw
       x_in = cur
       mid = x_in
-      # Blocks whose expanded map is large and whose depthwise is 3x3 stride 2 run the fused
-      # front half (expand in TMEM, depthwise from shared memory): measured faster than the two
-      # separate kernels on B200 (profiles/); the other blocks keep the two-kernel form.
+      # fuse_mbconv_front: blocks whose expanded map is large and whose depthwise is 3x3 stride 2
+      # run the fused front half (expand in TMEM, depthwise from shared memory; the expanded map
+      # never reaches HBM).  Off by default since round 2: with the three-team pointwise kernel
+      # and the TMA-tiled depthwise the separate pair is 1 % faster on the D0 step (4.165 vs
+      # 4.204 ms) although it moves 4x the bytes -- the fused kernel serialises TMA -> MMA ->
+      # epilogue -> depthwise inside a CTA at two CTAs per SM.
       fuse_front = (self.fuse_mbconv_front and b.expand_name and b.kernel_size == 3 and
                     b.stride == 2 and b.input_filters <= 64 and h * wd >= 1600)
       exp_wt = exp_b = None

@@ -122,6 +122,25 @@ def test_network_parity_lite3():
     assert rel_l2(got, orc.endpoints[b.name]) < REL_TOL
 
 
+def test_network_parity_fused_mbconv_front():
+  """The optional fused expand + depthwise kernel (Engine(fuse_mbconv_front=True)) in the network:
+  same bar, and block outputs equal to the default (separate kernels) engine to fp16 rounding."""
+  c, a, w, x = _setup('efficientdet-d0', 128, 2, seed=2)
+  orc = eo.Oracle(c, w, torch.float32)
+  orc(x)
+  fused = _engine(c, w, 2, use_cuda_graph=False, fuse_mbconv_front=True)
+  assert any(n.endswith('/expand_dw') for n in fused.op_names())
+  plain = _engine(c, w, 2, use_cuda_graph=False)
+  assert not any(n.endswith('/expand_dw') for n in plain.op_names())
+  fused.forward(torch.from_numpy(x))
+  plain.forward(torch.from_numpy(x))
+  torch.cuda.synchronize()
+  for b in a.blocks:
+    got = fused.buffers[b.name + '/out'].float().cpu().permute(0, 3, 1, 2)
+    assert rel_l2(got, orc.endpoints[b.name]) < REL_TOL, b.name
+    assert rel_l2(got, plain.buffers[b.name + '/out'].float().cpu().permute(0, 3, 1, 2)) < 5e-4, b.name
+
+
 def test_network_parity_d1_relu6():
   """A second backbone (b1) with the lite activation (relu6)."""
   c, a, w, x = _setup('efficientdet-d1', 128, 1, seed=3, act_type='relu6')
