@@ -36,17 +36,45 @@ from automl_b200.arch import DetArch
 from automl_b200.engine import Engine
 
 
-def load_weights(ckpt_path, arch, seed=0):
+EMA_SUFFIX = '/ExponentialMovingAverage'
+
+
+def resolve_checkpoint_names(ckpt_keys, wanted, ema_decay=0.9998):
+  """Maps model variable names to the keys of a checkpoint dump, the way the reference restores
+  (inference.restore_ckpt inference.py:193-230, tf2/util_keras.restore_ckpt util_keras.py:108-203):
+  with ema_decay > 0 every variable is read from its shadow `<name>/ExponentialMovingAverage` when
+  the checkpoint has one (trainable variables and the BN moving statistics all get shadows,
+  utils.get_ema_vars utils.py:78-87), else from `<name>`; a trailing ':0' on checkpoint keys is
+  ignored.  Returns {wanted name: checkpoint key}; missing variables are simply absent."""
+  norm = {}
+  for k in ckpt_keys:
+    norm.setdefault(k[:-2] if k.endswith(':0') else k, k)
+  out = {}
+  for name in wanted:
+    if ema_decay and ema_decay > 0 and name + EMA_SUFFIX in norm:
+      out[name] = norm[name + EMA_SUFFIX]
+    elif name in norm:
+      out[name] = norm[name]
+  return out
+
+
+def load_weights(ckpt_path, arch, seed=0, ema_decay=0.9998):
+  """'_' / None: seeded synthetic weights (the reference's "don't load a checkpoint" sentinel).
+  Otherwise an .npz whose keys are the reference's checkpoint variable names (Keras layouts):
+  either written directly, or dumped from a TF checkpoint with
+  scripts/export_tf_checkpoint_to_npz.py; EMA shadow variables are preferred like in the
+  reference (resolve_checkpoint_names)."""
   if ckpt_path == '_' or ckpt_path is None:
     return weights_lib.synthetic_weights(arch, seed)
   data = np.load(ckpt_path)
   specs = weights_lib.variable_specs(arch)
-  missing = [k for k in specs if k not in data]
+  names = resolve_checkpoint_names(list(data.keys()), specs, ema_decay)
+  missing = [k for k in specs if k not in names]
   if missing:
     raise ValueError('checkpoint %s lacks %d variables, e.g. %s' % (ckpt_path, len(missing), missing[:3]))
   out = {}
   for k, spec in specs.items():
-    v = np.asarray(data[k], np.float32)
+    v = np.asarray(data[names[k]], np.float32)
     if tuple(v.shape) != tuple(spec.shape):
       raise ValueError('variable %s has shape %s, expected %s' % (k, v.shape, spec.shape))
     out[k] = v
