@@ -22,7 +22,7 @@ constexpr int kFusePitch = kFuseCB + 4;
 // per input: the kernel is latency bound, ncu long-scoreboard 5.0 issue-slots per instruction).
 template <int ACT, int SIG>
 __global__ void __launch_bounds__(kFuseThreads)
-fuse_dw_kernel(const FuseParams p, const __half* __restrict__ dw_w, __half* __restrict__ out,
+fuse_dw_kernel(const FuseParams p, const float* __restrict__ dw_w, __half* __restrict__ out,
                int h, int wd, int c, int chunks) {
   pdl_launch_dependents();
   constexpr int HT = kFuseTH + 2, WT = kFuseTW + 2, G = kFuseCB / 8;
@@ -33,10 +33,10 @@ fuse_dw_kernel(const FuseParams p, const __half* __restrict__ dw_w, __half* __re
   const int c0 = (blockIdx.z % chunks) * kFuseCB;
   const int y0 = blockIdx.y * kFuseTH, x0 = blockIdx.x * kFuseTW;
   const int groups = min(G, (c - c0) >> 3);
-  // depthwise weights of this channel chunk as fp32 (constants: fetched before the PDL wait)
+  // fp32 depthwise weights of this channel chunk (constants: fetched before the PDL wait)
   for (int i = threadIdx.x; i < 9 * kFuseCB; i += kFuseThreads) {
     const int tap = i / kFuseCB, ch = i % kFuseCB;
-    wsm[i] = (c0 + ch < c) ? __half2float(__ldg(dw_w + static_cast<size_t>(tap) * c + c0 + ch)) : 0.f;
+    wsm[i] = (c0 + ch < c) ? __ldg(dw_w + static_cast<size_t>(tap) * c + c0 + ch) : 0.f;
   }
   pdl_wait_prior();
 
@@ -177,7 +177,7 @@ max_pool_kernel(const __half* __restrict__ in, __half* __restrict__ out, int h, 
 
 }  // namespace edet
 
-extern "C" int edet_fuse_dw(const edet_fuse_input* h_inputs, int n_inputs, const edet_half* dw_w,
+extern "C" int edet_fuse_dw(const edet_fuse_input* h_inputs, int n_inputs, const float* dw_w,
                             edet_half* out, int n, int h, int wd, int c, int act,
                             edet_stream_t stream) {
   using namespace edet;
@@ -187,7 +187,7 @@ extern "C" int edet_fuse_dw(const edet_fuse_input* h_inputs, int n_inputs, const
   if (int rc = fill_fuse_params(h_inputs, n_inputs, h, wd, "fuse_dw", &p)) return rc;
   const int chunks = ceil_div(c, kFuseCB);
   dim3 grid(ceil_div(wd, kFuseTW), ceil_div(h, kFuseTH), n * chunks);
-  const __half* hw = reinterpret_cast<const __half*>(dw_w);
+  const float* hw = dw_w;
   __half* ho = reinterpret_cast<__half*>(out);
   cudaStream_t s = as_stream(stream);
   cudaError_t err = cudaSuccess;

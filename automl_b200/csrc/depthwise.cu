@@ -30,7 +30,7 @@ struct DwCfg {
 template <int K, int S, int ACT, bool HAS_BIAS, bool HAS_SE>
 __global__ void __launch_bounds__(kDwThreads, (K == 3 || S == 1) ? 4 : 3)
 depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
-                 const __half* __restrict__ w, const float* __restrict__ bias,
+                 const float* __restrict__ w, const float* __restrict__ bias,
                  long long* __restrict__ se_sum, int h, int wd, int c, int ho, int wo, int pad_t,
                  int pad_l) {
   pdl_launch_dependents();
@@ -52,10 +52,10 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
   if (!active) pdl_wait_prior();
 
   if (active) {
-    const __half2* w2 = reinterpret_cast<const __half2*>(w);
+    const float2* w2 = reinterpret_cast<const float2*>(w);   // fp32 taps [k*k][c]
     float2 wreg[K * K];
 #pragma unroll
-    for (int t = 0; t < K * K; ++t) wreg[t] = __half22float2(__ldg(w2 + t * cp_count + cp));
+    for (int t = 0; t < K * K; ++t) wreg[t] = __ldg(w2 + t * cp_count + cp);
     pdl_wait_prior();   // the (constant) weights above were fetched during the previous kernel's tail
 
     float2 acc[ROWS][TW];
@@ -295,7 +295,7 @@ se_fc2_scale_kernel(const float* __restrict__ hidden, const float* __restrict__ 
 }
 
 template <int K, int S>
-static int launch_dw(const __half* in, __half* out, const __half* w, const float* bias,
+static int launch_dw(const __half* in, __half* out, const float* w, const float* bias,
                      long long* se_partial, int n, int h, int wd, int c, int act, cudaStream_t stream) {
   const int ho = ceil_div(h, S), wo = ceil_div(wd, S);
   const int pad_t = same_pad_before(h, K, S), pad_l = same_pad_before(wd, K, S);
@@ -322,12 +322,12 @@ static int launch_dw(const __half* in, __half* out, const __half* w, const float
 
 namespace dwt {   // depthwise_tile.cu
 bool eligible(int h, int wd, int c, int k, int stride);
-int run(const __half* in, __half* out, const __half* w, const float* bias, long long* se_sum,
+int run(const __half* in, __half* out, const float* w, const float* bias, long long* se_sum,
         int n, int h, int wd, int c, int k, int stride, int act, cudaStream_t stream);
 }  // namespace dwt
 }  // namespace edet
 
-extern "C" int edet_depthwise_conv(const edet_half* in, edet_half* out, const edet_half* w,
+extern "C" int edet_depthwise_conv(const edet_half* in, edet_half* out, const float* w,
                                    const float* bias, int64_t* se_sum, int n, int h, int wd,
                                    int c, int k, int stride, int act, edet_stream_t stream) {
   using namespace edet;
@@ -336,7 +336,7 @@ extern "C" int edet_depthwise_conv(const edet_half* in, edet_half* out, const ed
   EDET_CHECK_ARG((k == 3 || k == 5) && (stride == 1 || stride == 2),
                  "depthwise: k must be 3 or 5 and stride 1 or 2 (got %d, %d)", k, stride);
   const __half* hi = reinterpret_cast<const __half*>(in);
-  const __half* hw = reinterpret_cast<const __half*>(w);
+  const float* hw = w;
   __half* ho = reinterpret_cast<__half*>(out);
   long long* sp = reinterpret_cast<long long*>(se_sum);
   cudaStream_t s = as_stream(stream);

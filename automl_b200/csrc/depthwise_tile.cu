@@ -47,7 +47,7 @@ struct Cfg {
 struct Params {
   int n, h, w, c, ho, wo, pad_t, pad_l;
   int chunks, tiles_y, tiles_x, total_units;
-  const __half* wgt;      // [k*k][c]
+  const float* wgt;       // fp32 taps [k*k][c]
   const float* bias;      // [c] or null
   __half* out;            // [n, ho, wo, c]
   long long* se_sum;      // [n, c] or null
@@ -144,10 +144,10 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
     const bool lane_ok = cp < cp_total;
     if (un.chunk != cur_chunk) {                                 // (re)load this slice's weights
       cur_chunk = un.chunk;
-      const __half2* w2 = reinterpret_cast<const __half2*>(p.wgt);
+      const float2* w2 = reinterpret_cast<const float2*>(p.wgt);
 #pragma unroll
       for (int t = 0; t < K * K; ++t)
-        wreg[t] = lane_ok ? __half22float2(__ldg(w2 + t * cp_total + cp)) : make_float2(0.f, 0.f);
+        wreg[t] = lane_ok ? __ldg(w2 + t * cp_total + cp) : make_float2(0.f, 0.f);
       if (HAS_BIAS) bv = lane_ok ? __ldg(reinterpret_cast<const float2*>(p.bias) + cp) : make_float2(0.f, 0.f);
     }
     mbar_wait(smem_u32(&bars[stage]), phase);                    // the tile has landed
@@ -274,7 +274,7 @@ bool eligible(int h, int wd, int c, int k, int stride) {
 }
 
 template <int K, int S>
-static int run_ks(const __half* in, __half* out, const __half* w, const float* bias,
+static int run_ks(const __half* in, __half* out, const float* w, const float* bias,
                   long long* se_sum, int n, int h, int wd, int c, int act, cudaStream_t stream) {
   using C = Cfg<K, S>;
   Params p;
@@ -298,7 +298,7 @@ static int run_ks(const __half* in, __half* out, const __half* w, const float* b
   return launch_kernel<K, S>(mx, p, grid, act, stream);
 }
 
-int run(const __half* in, __half* out, const __half* w, const float* bias, long long* se_sum,
+int run(const __half* in, __half* out, const float* w, const float* bias, long long* se_sum,
         int n, int h, int wd, int c, int k, int stride, int act, cudaStream_t stream) {
   if (k == 3 && stride == 1) return run_ks<3, 1>(in, out, w, bias, se_sum, n, h, wd, c, act, stream);
   if (k == 3 && stride == 2) return run_ks<3, 2>(in, out, w, bias, se_sum, n, h, wd, c, act, stream);

@@ -56,7 +56,7 @@ struct Params {
   int tiles_y, tiles_x, total_tiles;
   int tmem_cols;
   const float* bias_e;         // [cmid]
-  const __half* wd;            // [k*k][cmid]
+  const float* wd;             // fp32 depthwise taps [k*k][cmid]
   const float* bias_d;         // [cmid]
   __half* out;                 // [n, ho, wo, cmid]
   long long* se_sum;           // [n, cmid] or null
@@ -236,10 +236,10 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
         constexpr int IN_R = (OTW - 1) * S + K, IN_C = (CG - 1) * S + K;
         for (int item = threadIdx.x; item < NCG * cpn; item += kThreads) {
           const int xg = item / cpn, cp = item - xg * cpn;
-          const __half2* wd2 = reinterpret_cast<const __half2*>(p.wd) + ((cbase >> 1) + cp);
+          const float2* wd2 = reinterpret_cast<const float2*>(p.wd) + ((cbase >> 1) + cp);
           float2 wk[K * K];
 #pragma unroll
-          for (int i = 0; i < K * K; ++i) wk[i] = __half22float2(__ldg(wd2 + i * cm2));
+          for (int i = 0; i < K * K; ++i) wk[i] = __ldg(wd2 + i * cm2);
           uint32_t coff[IN_C];     // the last column group reads a clamped (discarded) column
 #pragma unroll
           for (int j = 0; j < IN_C; ++j)
@@ -295,7 +295,7 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
       // one (output row, channel pair) per work item
       for (int item = threadIdx.x; item < rows * cpn; item += kThreads) {
         const int oyl = item / cpn, cp = item - oyl * cpn;
-        const __half2* wd2 = reinterpret_cast<const __half2*>(p.wd) + ((cbase >> 1) + cp);
+        const float2* wd2 = reinterpret_cast<const float2*>(p.wd) + ((cbase >> 1) + cp);
         const uint32_t ebase = e_u32 + (oyl * S * kPatch) * kEPitch + cp * 4;
         float2 acc[OTW];
 #pragma unroll
@@ -304,7 +304,7 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap map_x,
         for (int ky = 0; ky < K; ++ky) {
           float2 wk[K];
 #pragma unroll
-          for (int kx = 0; kx < K; ++kx) wk[kx] = __half22float2(__ldg(wd2 + (ky * K + kx) * cm2));
+          for (int kx = 0; kx < K; ++kx) wk[kx] = __ldg(wd2 + (ky * K + kx) * cm2);
 #pragma unroll
           for (int ixl = 0; ixl < NIX; ++ixl) {
             const float2 v = h2_bits_to_f2(lds_b32(ebase + (ky * kPatch + ixl) * kEPitch));
@@ -386,7 +386,7 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p,
 }  // namespace edet
 
 extern "C" int edet_mbconv_expand_dw(const edet_half* x, const edet_half* we, const float* bias_e,
-                                     const edet_half* wd, const float* bias_d, edet_half* out,
+                                     const float* wd, const float* bias_d, edet_half* out,
                                      int64_t* se_sum, int n, int h, int w, int cin, int cmid,
                                      int k, int stride, int act, edet_stream_t stream) {
   using namespace edet;
@@ -422,7 +422,7 @@ extern "C" int edet_mbconv_expand_dw(const edet_half* x, const edet_half* we, co
   p.desc_layout = p.block_k == 64 ? 2 : (p.block_k == 32 ? 4 : 6);
   p.desc_sbo = 8 * p.block_k * 2;
   p.bias_e = bias_e; p.bias_d = bias_d;
-  p.wd = reinterpret_cast<const __half*>(wd);
+  p.wd = wd;
   p.out = reinterpret_cast<__half*>(out);
   p.se_sum = reinterpret_cast<long long*>(se_sum);
   p.sched = next_sched_slot();

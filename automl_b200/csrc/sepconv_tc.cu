@@ -35,7 +35,7 @@ constexpr int kAtomBytesA = 128 * 128;    // [128 rows][64 halves]
 
 struct Params {
   FuseParams fuse;
-  const __half* dw_w;     // [9][c]
+  const float* dw_w;      // fp32 taps [9][c]
   const float* bias;      // [nout]
   __half* out;            // [n, h, w, ldo]
   int n, h, w, c, nout, ldo;
@@ -146,9 +146,10 @@ sepconv_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
           for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-              float wf[8];
-              half8_to_float(__ldg(reinterpret_cast<const uint4*>(
-                                 p.dw_w + static_cast<size_t>(ky * 3 + kx) * c + ch)), wf);
+              const float4* wp4 = reinterpret_cast<const float4*>(
+                  p.dw_w + static_cast<size_t>(ky * 3 + kx) * c + ch);
+              const float4 w0 = __ldg(wp4), w1 = __ldg(wp4 + 1);
+              const float wf[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
               const float4* src =
                   reinterpret_cast<const float4*>(fused + ((ty + ky) * WT + tx + kx) * CB + g * 8);
               const float4 a = src[0], b = src[1];
@@ -294,7 +295,7 @@ sepconv_direct_kernel(const __grid_constant__ CUtensorMap map_w, const Params p)
   const int cp_count = c >> 1;
   const int items = 4 * cp_count;   // (4-column group, channel pair)
   const FuseIn& src = p.fuse.in[0];
-  const __half2* w2 = reinterpret_cast<const __half2*>(p.dw_w);
+  const float2* w2 = reinterpret_cast<const float2*>(p.dw_w);
   pdl_wait_prior();
 
   const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(p.npad >> 3) << 17) |
@@ -317,7 +318,7 @@ sepconv_direct_kernel(const __grid_constant__ CUtensorMap map_w, const Params p)
       const int xg = e / cp_count, cp = e - xg * cp_count;
       float2 wreg[9];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) wreg[i] = __half22float2(__ldg(w2 + i * cp_count + cp));
+      for (int i = 0; i < 9; ++i) wreg[i] = __ldg(w2 + i * cp_count + cp);
       float2 acc[TH][4];
 #pragma unroll
       for (int r = 0; r < TH; ++r)
@@ -534,7 +535,7 @@ sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
   const int c = p.c, h = p.h, wd = p.w;
   const int cp_count = c >> 1;
   const int items = 4 * cp_count;   // (4-column group, channel pair)
-  const __half2* w2 = reinterpret_cast<const __half2*>(p.dw_w);
+  const float2* w2 = reinterpret_cast<const float2*>(p.dw_w);
   pdl_wait_prior();
 
   auto fetch_tile = [&](int tile, int slot) {          // thread 0 only
@@ -573,7 +574,7 @@ sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
       const int xg = e / cp_count, cp = e - xg * cp_count;
       float2 wreg[9];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) wreg[i] = __half22float2(__ldg(w2 + i * cp_count + cp));
+      for (int i = 0; i < 9; ++i) wreg[i] = __ldg(w2 + i * cp_count + cp);
       float2 acc[TH][4];
 #pragma unroll
       for (int r = 0; r < TH; ++r)
@@ -719,7 +720,7 @@ static int launch(const CUtensorMap& mw, const Params& p, int grid, int smem_byt
 }  // namespace edet
 
 extern "C" int edet_sepconv(const edet_fuse_input* h_inputs, int n_inputs, int pre_act,
-                            const edet_half* dw_w, const edet_half* pw_wt, const float* bias,
+                            const float* dw_w, const edet_half* pw_wt, const float* bias,
                             edet_half* out, int ldo, int n, int h, int wd, int c, int nout,
                             int post_act, edet_stream_t stream) {
   using namespace edet;
@@ -732,7 +733,7 @@ extern "C" int edet_sepconv(const edet_fuse_input* h_inputs, int n_inputs, int p
                  nout, ldo);
   Params p;
   if (int rc = fill_fuse_params(h_inputs, n_inputs, h, wd, "sepconv", &p.fuse)) return rc;
-  p.dw_w = reinterpret_cast<const __half*>(dw_w);
+  p.dw_w = dw_w;
   p.bias = bias;
   p.out = reinterpret_cast<__half*>(out);
   p.n = n; p.h = h; p.w = wd; p.c = c; p.nout = nout; p.ldo = ldo;

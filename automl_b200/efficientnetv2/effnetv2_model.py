@@ -286,7 +286,7 @@ class EffNetV2Model(object):
                     flops=2 * b.input_filters * mid.numel())
         s, sh = _bn_fold(w, '%s/%s' % (sc, next(bns)), eps)
         kd = np.asarray(w[sc + '/depthwise_conv2d/depthwise_kernel'], np.float64)[..., 0] * s
-        dw_w, dw_b = self._dev(kd.reshape(b.kernel_size**2, -1), f16), self._dev(sh, f32)
+        dw_w, dw_b = self._dev(kd.reshape(b.kernel_size**2, -1), f32), self._dev(sh, f32)   # fp32 taps
         dwo = buf((n, ho, wo, b.mid_filters))
         partial = next_zero = None
         if b.se_filters:

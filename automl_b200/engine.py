@@ -183,7 +183,7 @@ class Engine(object):
       # depthwise
       s, sh = _bn_fold(w, '%s/%s' % (scope, b.dw_bn), eps)
       kd = np.asarray(w[scope + '/depthwise_conv2d/depthwise_kernel'], np.float64)[..., 0]  # [k,k,C]
-      dw_w = self._dev((kd * s).reshape(b.kernel_size * b.kernel_size, -1), f16)
+      dw_w = self._dev((kd * s).reshape(b.kernel_size * b.kernel_size, -1), f32)   # fp32 taps
       dw_b = self._dev(sh, f32)
       ho, wo = utils.same_pad(h, b.kernel_size, b.stride)[0], utils.same_pad(wd, b.kernel_size, b.stride)[0]
       dwo = self._buf(b.name + '/dw', (n, ho, wo, b.mid_filters))
@@ -334,7 +334,7 @@ class Engine(object):
             needs.append('~' + r.scope)
           specs.append((src, mode_code[r.mode], r.pool, float(wgt)))
         op = node.op_scope
-        dw_w = self._dev(np.asarray(w[op + '/conv/depthwise_kernel'], np.float64)[..., 0].reshape(9, F), f16)
+        dw_w = self._dev(np.asarray(w[op + '/conv/depthwise_kernel'], np.float64)[..., 0].reshape(9, F), f32)
         s, sh = _bn_fold(w, op + '/bn', eps)
         kp = np.asarray(w[op + '/conv/pointwise_kernel'], np.float64)[0, 0]
         cb = np.asarray(w[op + '/conv/bias'], np.float64)
@@ -369,11 +369,11 @@ class Engine(object):
       dws, pws, pbs = [], [], []
       for i in range(a.head_repeats):
         name = '%s/%s-%d' % (scope, net, i)
-        dws.append(self._dev(np.asarray(w[name + '/depthwise_kernel'], np.float64)[..., 0].reshape(9, F), f16))
+        dws.append(self._dev(np.asarray(w[name + '/depthwise_kernel'], np.float64)[..., 0].reshape(9, F), f32))
         pws.append(np.asarray(w[name + '/pointwise_kernel'], np.float64)[0, 0])
         pbs.append(np.asarray(w[name + '/bias'], np.float64))
       name = '%s/%s-predict' % (scope, net)
-      pred_dw = self._dev(np.asarray(w[name + '/depthwise_kernel'], np.float64)[..., 0].reshape(9, F), f16)
+      pred_dw = self._dev(np.asarray(w[name + '/depthwise_kernel'], np.float64)[..., 0].reshape(9, F), f32)
       pred_wt = self._dev(np.asarray(w[name + '/pointwise_kernel'], np.float64)[0, 0].T, f16)  # [pred_c, F]
       pred_b = self._dev(w[name + '/bias'], f32)
       for level in a.levels:

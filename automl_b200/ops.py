@@ -82,7 +82,7 @@ def depthwise_conv(x, out, w, bias, act, k, stride, se_sum=None):
   """se_sum: int64 [N, C] accumulator (added to; 2^-20 fixed point) or None."""
   n, h, wd, c = x.shape
   _lib.call('edet_depthwise_conv', _ptr(x, torch.float16), _ptr(out, torch.float16),
-            _ptr(w, torch.float16), _ptr(bias, torch.float32), _ptr(se_sum, torch.int64),
+            _ptr(w, torch.float32), _ptr(bias, torch.float32), _ptr(se_sum, torch.int64),
             n, h, wd, c, k, stride, act, _stream())
 
 
@@ -97,12 +97,12 @@ def conv2d(x, wt, bias, out, act, ksize, stride, residual=None):
 
 
 def mbconv_expand_dw(x, we, bias_e, wd, bias_d, out, act, k, stride, se_sum=None):
-  """Fused expand 1x1 + depthwise kxk: x fp16 [N,H,W,cin], we fp16 [cmid,cin], wd fp16
+  """Fused expand 1x1 + depthwise kxk: x fp16 [N,H,W,cin], we fp16 [cmid,cin], wd fp32
   [k*k,cmid], out fp16 [N,Ho,Wo,cmid]; se_sum int64 [N,cmid] (added to) or None."""
   n, h, wd_, cin = x.shape
   cmid = we.shape[0]
   _lib.call('edet_mbconv_expand_dw', _ptr(x, torch.float16), _ptr(we, torch.float16),
-            _ptr(bias_e, torch.float32), _ptr(wd, torch.float16), _ptr(bias_d, torch.float32),
+            _ptr(bias_e, torch.float32), _ptr(wd, torch.float32), _ptr(bias_d, torch.float32),
             _ptr(out, torch.float16), _ptr(se_sum, torch.int64), n, h, wd_, cin, cmid, k, stride,
             act, _stream())
 
@@ -143,7 +143,7 @@ def fuse_dw(specs, dw_w, out, act):
   for t, _, _, _ in specs:
     _ptr(t, torch.float16)
   arr = make_fuse_inputs(specs)
-  _lib.call('edet_fuse_dw', arr, len(specs), _ptr(dw_w, torch.float16),
+  _lib.call('edet_fuse_dw', arr, len(specs), _ptr(dw_w, torch.float32),
             _ptr(out, torch.float16), n, h, wd, c, act, _stream())
 
 
@@ -159,7 +159,7 @@ def sepconv(specs, pre_act, dw_w, pw_wt, bias, out, post_act, nout=None):
   for t, _, _, _ in specs:
     _ptr(t, torch.float16)
   arr = make_fuse_inputs(specs)
-  _lib.call('edet_sepconv', arr, len(specs), pre_act, _ptr(dw_w, torch.float16),
+  _lib.call('edet_sepconv', arr, len(specs), pre_act, _ptr(dw_w, torch.float32),
             _ptr(pw_wt, torch.float16), _ptr(bias, torch.float32), _ptr(out, torch.float16), ldo,
             n, h, wd, c, n_out, post_act, _stream())
 

@@ -107,11 +107,11 @@ int edet_conv2d(const edet_half* in, const edet_half* wt, const float* bias,
  * Replaces: backbone/efficientnet_model.py:303-333 (the two convs + BNs), :387-391 (their use in
  * MBConvBlock._call) and the reduce_mean of :192.
  *   x [n,h,w,cin] fp16 (cin % 8 == 0), we [cmid][cin] fp16, bias_e [cmid] f32,
- *   wd [k*k][cmid] fp16, bias_d [cmid] f32, out [n,ceil(h/stride),ceil(w/stride),cmid] fp16,
+ *   wd [k*k][cmid] float32, bias_d [cmid] f32, out [n,ceil(h/stride),ceil(w/stride),cmid] fp16,
  *   se_sum int64 [n][cmid] (2^-20 fixed point, ADDED to) or NULL; k in {3,5}, stride in {1,2},
  *   act in {EDET_ACT_SWISH, EDET_ACT_RELU6} applied after both convs (as the reference does). */
 int edet_mbconv_expand_dw(const edet_half* x, const edet_half* we, const float* bias_e,
-                          const edet_half* wd, const float* bias_d, edet_half* out,
+                          const float* wd, const float* bias_d, edet_half* out,
                           int64_t* se_sum, int n, int h, int w, int cin, int cmid, int k,
                           int stride, int act, edet_stream_t stream);
 
@@ -141,11 +141,12 @@ int edet_pointwise_conv(const edet_half* a, int lda, const edet_half* wt, int wb
  * Replaces DepthwiseConv2D + BN + swish  backbone/efficientnet_model.py:320-333, 391 and the
  * depthwise half of SeparableConv2D  efficientdet_arch.py:149-191, 206-249 (bias NULL, act NONE).
  *   in   half [n, h, w, c]     out  half [n, ceil(h/s), ceil(w/s), c]
- *   w    half [k*k][c] (BN scale folded)        bias float32 [c] or NULL
+ *   w    float32 [k*k][c] (BN scale folded; the taps stay fp32: a depthwise tap error is not
+ *        averaged over a K dimension like a GEMM weight's)      bias float32 [c] or NULL
  *   se_sum  int64 [n, c] or NULL: ADDED to (caller zeroes it), 2^-20 fixed point, so the
  *           reduction is order independent and bit-reproducible
  */
-int edet_depthwise_conv(const edet_half* in, edet_half* out, const edet_half* w,
+int edet_depthwise_conv(const edet_half* in, edet_half* out, const float* w,
                         const float* bias, int64_t* se_sum, int n, int h, int wd, int c, int k,
                         int stride, int act, edet_stream_t stream);
 
@@ -183,7 +184,7 @@ typedef struct {
   int pool_h, pool_w, stride_h, stride_w; /* EDET_RS_DOWN only */
   float weight;         /* normalised fusion weight of this input */
 } edet_fuse_input;
-int edet_fuse_dw(const edet_fuse_input* h_inputs, int n_inputs, const edet_half* dw_w,
+int edet_fuse_dw(const edet_fuse_input* h_inputs, int n_inputs, const float* dw_w,
                  edet_half* out, int n, int h, int wd, int c, int act, edet_stream_t stream);
 
 /* Fused separable convolution of the feature network / head towers (tcgen05):
@@ -194,9 +195,9 @@ int edet_fuse_dw(const edet_fuse_input* h_inputs, int n_inputs, const edet_half*
  * network activation, post_act = NONE) or a head tower layer (:149-191 / :206-249: one input,
  * weight 1, pre_act = NONE, post_act = the activation after the per-level BN folded into
  * pw_wt / bias).
- *   dw_w half [9][c], pw_wt half [nout][c], bias float32 [nout], out half [n,h,wd,ldo]
+ *   dw_w float32 [9][c], pw_wt half [nout][c], bias float32 [nout], out half [n,h,wd,ldo]
  *   c % 8 == 0, c <= 128; nout % 8 == 0, nout <= 128; ldo >= nout, ldo % 8 == 0. */
-int edet_sepconv(const edet_fuse_input* h_inputs, int n_inputs, int pre_act, const edet_half* dw_w,
+int edet_sepconv(const edet_fuse_input* h_inputs, int n_inputs, int pre_act, const float* dw_w,
                  const edet_half* pw_wt, const float* bias, edet_half* out, int ldo, int n, int h,
                  int wd, int c, int nout, int post_act, edet_stream_t stream);
 

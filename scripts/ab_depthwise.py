@@ -28,7 +28,7 @@ def main():
   for name, n, h, w, c, k, s, se in SHAPES:
     g = torch.Generator().manual_seed(1)
     x = torch.randn(n, h, w, c, generator=g).half().to(DEV)
-    wk = (torch.randn(k * k, c, generator=g) / k).half().to(DEV)
+    wk = (torch.randn(k * k, c, generator=g) / k).to(DEV)
     bias = (torch.randn(c, generator=g) * 0.1).to(DEV) if se else None
     ho, wo = -(-h // s), -(-w // s)
     out = torch.empty(n, ho, wo, c, dtype=torch.float16, device=DEV)

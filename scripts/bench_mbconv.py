@@ -41,7 +41,7 @@ for name, h, cin, cmid, k, s in SHAPES:
   x = torch.randn(N, h, h, cin, generator=g).half().to(DEV)
   we = (torch.randn(cmid, cin, generator=g) / cin**0.5).half().to(DEV)
   be = (torch.randn(cmid, generator=g) * 0.2).to(DEV)
-  wk = (torch.randn(k * k, cmid, generator=g) / k).half().to(DEV)
+  wk = (torch.randn(k * k, cmid, generator=g) / k).to(DEV)
   bd = (torch.randn(cmid, generator=g) * 0.1).to(DEV)
   ho = -(-h // s)
   e = torch.empty(N, h, h, cmid, dtype=torch.float16, device=DEV)

@@ -15,7 +15,7 @@ N = 32
 
 def dw(h, c, k, s, se=True):
   x = torch.randn(N, h, h, c, device=dev).half()
-  w = torch.randn(k * k, c, device=dev).half()
+  w = torch.randn(k * k, c, device=dev)
   b = torch.randn(c, device=dev)
   ho = -(-h // s)
   out = torch.empty(N, ho, ho, c, dtype=torch.float16, device=dev)
@@ -47,7 +47,7 @@ def front(h, cin, cmid, k, s):
   x = torch.randn(N, h, h, cin, device=dev).half()
   we = (torch.randn(cmid, cin, device=dev) / cin**0.5).half()
   be = torch.randn(cmid, device=dev) * 0.1
-  wd = (torch.randn(k * k, cmid, device=dev) / k).half()
+  wd = torch.randn(k * k, cmid, device=dev) / k
   bd = torch.randn(cmid, device=dev) * 0.1
   ho = -(-h // s)
   out = torch.empty(N, ho, ho, cmid, dtype=torch.float16, device=dev)
@@ -58,7 +58,7 @@ def front(h, cin, cmid, k, s):
 
 def tower(h, f=64):
   x = torch.randn(N, h, h, f, device=dev).half()
-  dwk = (torch.randn(9, f, device=dev) / 3).half()
+  dwk = torch.randn(9, f, device=dev) / 3
   pwk = (torch.randn(f, f, device=dev) / f**0.5).half()
   b = torch.randn(f, device=dev) * 0.1
   out = torch.empty(N, h, h, f, dtype=torch.float16, device=dev)
@@ -69,7 +69,7 @@ def tower(h, f=64):
 def node(h, f=64):
   a = torch.randn(N, h, h, f, device=dev).half()
   u = torch.randn(N, h // 2, h // 2, f, device=dev).half()
-  dwk = (torch.randn(9, f, device=dev) / 3).half()
+  dwk = torch.randn(9, f, device=dev) / 3
   out = torch.empty(N, h, h, f, dtype=torch.float16, device=dev)
   for _ in range(reps):
     ops.fuse_dw([(a, ops.RS_SAME, None, 0.6), (u, ops.RS_UP, None, 0.4)], dwk, out, utils.ACT_SWISH)

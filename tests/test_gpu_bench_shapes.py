@@ -119,17 +119,29 @@ def test_d4_1024():
 
 def test_d7x_1536():
   """BASELINE config 5.  55 MBConv blocks and 8 un-normalised 'sum' BiFPN cells on random
-  weights: this model does NOT meet the 1e-3 bar with fp16 activation / weight storage.
-  Measured on B200 (round 2): blocks 2.8e-3, BiFPN 3.1e-3, class outputs 4.2e-3, box outputs
-  5.2e-3.  The oracle's own storage model (fp32 arithmetic, tensors rounded to fp16 where the
-  engine stores them) already gives 1.3e-3 / 1.9e-3 at 256x256; DESIGN.md section 6 has the
-  per-rounding-site budget (residual stream 1.05e-3, each of expand / depthwise / block-input
-  stores 0.5e-3, fp16 weights as much again) and why only a split-precision (fp16 hi + lo)
-  storage mode -- not built -- can reach 1e-3 here.  The bars below are regression guards at
-  ~1.2x the measured values, NOT the north_star tolerance."""
-  _, _, _, _, errs = _network_errors('efficientdet-d7x', 1536, 1)
+  weights: this model does NOT meet the 1e-3 bar with fp16 activation / weight storage, kernels
+  aside -- the fp32 oracle with nothing but the engine's rounding sites applied (fp16 tensors in
+  HBM, BN folded into fp16 GEMM weights: tests/precision_model.py) is itself that far from the
+  plain fp32 oracle.  DESIGN.md section 6 has the per-rounding-site budget and why only a
+  split-precision (fp16 hi + lo) storage mode -- not built -- can reach 1e-3 here.  Asserted: every
+  tensor within 1.5x the format model + 1e-4 (the kernels add nothing beyond the format), plus
+  absolute regression guards."""
+  import precision_model as pm
+  c, a, eng, x, errs = _network_errors('efficientdet-d7x', 1536, 1)
+  w = weights.synthetic_weights(a, 0)
+  model = eo.Oracle(c, pm.device_weights(a, w), torch.float32, store=eo.fp16_store)
+  cls_m, box_m = model(x)
+  ref = eo.Oracle(c, w, torch.float32)
+  cls_r, box_r = ref(x)
+  merr = {'blocks': {b.name: rel_l2(model.endpoints[b.name], ref.endpoints[b.name]) for b in a.blocks},
+          'fpn': {str(l): rel_l2(model.endpoints['fpn_%d' % l], ref.endpoints['fpn_%d' % l]) for l in a.levels},
+          'cls': {str(l): rel_l2(cls_m[l], cls_r[l]) for l in a.levels},
+          'box': {str(l): rel_l2(box_m[l], box_r[l]) for l in a.levels}}
   worst = _worst(errs)
-  _record('efficientdet-d7x 1536x1536 batch 1', worst)
+  _record('efficientdet-d7x 1536x1536 batch 1', dict(worst, format_model=_worst(merr)))
+  for group in errs:
+    for k, dev in errs[group].items():
+      assert dev < pm.bar(merr[group][k]), (group, k, dev, merr[group][k])
   assert worst['blocks'] < 3.5e-3, errs['blocks']
   assert worst['fpn'] < 3.8e-3, errs['fpn']
   assert worst['cls'] < 5e-3, errs['cls']

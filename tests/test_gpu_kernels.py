@@ -168,7 +168,7 @@ def test_depthwise_conv(case):
   partial = None
   if has_se:
     partial = torch.zeros(n, c, dtype=torch.int64, device=DEV)   # 2^-20 fixed-point sums
-  ops.depthwise_conv(x.to(DEV), out, wk.reshape(k * k, c).to(DEV),
+  ops.depthwise_conv(x.to(DEV), out, wk.reshape(k * k, c).float().to(DEV),
                      bias.to(DEV) if has_bias else None, act, k, s, partial)
   torch.cuda.synchronize()
   ref = eo.depthwise_conv2d_same(x.double().permute(0, 3, 1, 2), wk.double().unsqueeze(-1), s)
@@ -183,7 +183,7 @@ def test_depthwise_conv(case):
     np.testing.assert_allclose(sums.numpy(), ref.sum((1, 2)).numpy(), rtol=1e-4, atol=1e-3)
     # the squeeze is order independent: a second run gives the identical integers
     again = torch.zeros_like(partial)
-    ops.depthwise_conv(x.to(DEV), out, wk.reshape(k * k, c).to(DEV),
+    ops.depthwise_conv(x.to(DEV), out, wk.reshape(k * k, c).float().to(DEV),
                        bias.to(DEV) if has_bias else None, act, k, s, again)
     torch.cuda.synchronize()
     assert torch.equal(again, partial)
@@ -198,7 +198,7 @@ def test_depthwise_tiled_equals_register_kernel(case):
   n, h, w, c, k, s, act, has_bias, has_se = case
   g = torch.Generator().manual_seed(7 + h + c)
   x = torch.randn(n, h, w, c, generator=g).half().to(DEV)
-  wk = (torch.randn(k * k, c, generator=g) / k).half().to(DEV)
+  wk = (torch.randn(k * k, c, generator=g) / k).to(DEV)   # fp32 taps
   bias = (torch.randn(c, generator=g) * 0.1).to(DEV) if has_bias else None
   ho, wo = -(-h // s), -(-w // s)
   outs, sums = [], []
@@ -248,7 +248,7 @@ def test_mbconv_expand_dw(case):
   ho, wo = -(-h // s), -(-w // s)
   out = torch.full((n, ho, wo, cmid), 7.0, dtype=torch.float16, device=DEV)
   se = torch.zeros(n, cmid, dtype=torch.int64, device=DEV) if has_se else None
-  args = (x.to(DEV), we.to(DEV), be.to(DEV), wk.reshape(k * k, cmid).to(DEV), bd.to(DEV))
+  args = (x.to(DEV), we.to(DEV), be.to(DEV), wk.reshape(k * k, cmid).float().to(DEV), bd.to(DEV))
   ops.mbconv_expand_dw(*args, out, act, k, s, se)
   torch.cuda.synchronize()
   # reference: the expanded map is an fp16 tensor (as in the unfused pipeline)
@@ -338,7 +338,7 @@ def test_fuse_dw_all_modes():
     out = torch.empty(n, h, w, c, dtype=torch.float16, device=DEV)
     specs = [(same.to(DEV), ops.RS_SAME, None, wts[0]), (up.to(DEV), ops.RS_UP, None, wts[1]),
              (down.to(DEV), ops.RS_DOWN, (3, 3, 2, 2), wts[2])]
-    ops.fuse_dw(specs, dwk.reshape(9, c).to(DEV), out, utils.ACT_SWISH)
+    ops.fuse_dw(specs, dwk.reshape(9, c).float().to(DEV), out, utils.ACT_SWISH)
     torch.cuda.synchronize()
     nchw = lambda t: t.double().permute(0, 3, 1, 2)
     fused = (nchw(same) * np.float32(wts[0]) + eo.resize_nearest_tf1(nchw(up), h, w) * np.float32(wts[1]) +
@@ -378,7 +378,7 @@ def test_fuse_dw_bifpn_signatures(sig, hw):
   dwk = (torch.randn(3, 3, c, generator=g) / 3).half()
   out = torch.empty(n, h, w, c, dtype=torch.float16, device=DEV)
   specs = [(t.to(DEV), m, pool, wt) for t, (m, pool), wt in zip(tens, modes, wts)]
-  ops.fuse_dw(specs, dwk.reshape(9, c).to(DEV), out, utils.ACT_SWISH)
+  ops.fuse_dw(specs, dwk.reshape(9, c).float().to(DEV), out, utils.ACT_SWISH)
   torch.cuda.synchronize()
   fused = sum(r * np.float32(wt) for r, wt in zip(res, wts))
   fused = fused * torch.sigmoid(fused)
@@ -470,10 +470,10 @@ def test_sepconv(case, impl):
   bias = torch.randn(nout, generator=g) * 0.1
   ldo = nout + 8
   out = torch.full((n, h, w, ldo), 7.0, dtype=torch.float16, device=DEV)
-  ops.sepconv(specs, pre, dw_w.to(DEV), pw.to(DEV), bias.to(DEV), out, post, nout=nout)
+  ops.sepconv(specs, pre, dw_w.float().to(DEV), pw.to(DEV), bias.to(DEV), out, post, nout=nout)
   tmp = torch.empty(n, h, w, c, dtype=torch.float16, device=DEV)
   two = torch.full((n, h, w, ldo), 7.0, dtype=torch.float16, device=DEV)
-  ops.fuse_dw(specs, dw_w.to(DEV), tmp, pre)
+  ops.fuse_dw(specs, dw_w.float().to(DEV), tmp, pre)
   ops.pointwise_conv(tmp, pw.to(DEV), bias.to(DEV), two, post, rows=n * h * w, nout=nout)
   torch.cuda.synchronize()
   ops.set_option('sepconv_impl', 0)

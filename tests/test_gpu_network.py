@@ -12,6 +12,7 @@ from automl_b200 import arch
 from automl_b200 import hparams_config
 from automl_b200 import weights
 from oracle import efficientdet_oracle as eo
+import precision_model as pm
 from oracle import postprocess_oracle as po
 
 pytestmark = pytest.mark.gpu
@@ -69,17 +70,10 @@ def test_network_parity(name, image_size, n, impl):
     assert float((gb - box_ref[l]).abs().max()) < 5e-3
 
 
-@pytest.mark.parametrize('name,size,bb_tol,head_tol', [
-    ('efficientdet-d4', 256, 1e-3, 1e-3),      # BASELINE config 4 (B4 backbone, F = 224, 7 cells)
-    ('efficientdet-d7x', 256, 3e-3, 3.5e-3),   # BASELINE config 5 (B7, levels 3-8, F = 384, 'sum')
-])
-def test_network_parity_baseline_configs(name, size, bb_tol, head_tol):
-  """The models of BASELINE.json's configs 4 and 5 at a reduced image size.  D4 is within the
-  1e-3 bar everywhere (measured 7.5e-4 worst backbone block, <= 5.3e-4 on the heads).  D7x stacks
-  55 MBConv blocks and 8 un-normalised 'sum' BiFPN cells on random weights: measured 2.1e-3 on the
-  last backbone block and up to 2.8e-3 on a box output (fp16 rounding of the residual stream
-  accumulates as a random walk; DESIGN.md section 6 open item) -- held to 3e-3 / 3.5e-3."""
-  c, a, w, x = _setup(name, size, 1)
+def test_network_parity_d4_reduced():
+  """The model of BASELINE.json's config 4 (B4 backbone, F = 224, 7 cells) at a reduced image size:
+  inside the 1e-3 bar everywhere (the full 1024 x 1024 shape is in test_gpu_bench_shapes.py)."""
+  c, a, w, x = _setup('efficientdet-d4', 256, 1)
   orc = eo.Oracle(c, w, torch.float32)
   cls_ref, box_ref = orc(x)
   eng = _engine(c, w, 1, use_cuda_graph=False)
@@ -87,36 +81,66 @@ def test_network_parity_baseline_configs(name, size, bb_tol, head_tol):
   torch.cuda.synchronize()
   for b in a.blocks:
     got = eng.buffers[b.name + '/out'].float().cpu().permute(0, 3, 1, 2)
-    assert rel_l2(got, orc.endpoints[b.name]) < bb_tol, b.name
+    assert rel_l2(got, orc.endpoints[b.name]) < REL_TOL, b.name
   for l in a.levels:
-    assert rel_l2(eng.fpn_feats[l].float().cpu().permute(0, 3, 1, 2), orc.endpoints['fpn_%d' % l]) < head_tol
-    assert rel_l2(cls_out[l].float().cpu(), cls_ref[l]) < head_tol, 'cls %d' % l
-    assert rel_l2(box_out[l].float().cpu(), box_ref[l]) < head_tol, 'box %d' % l
+    assert rel_l2(eng.fpn_feats[l].float().cpu().permute(0, 3, 1, 2), orc.endpoints['fpn_%d' % l]) < REL_TOL
+    assert rel_l2(cls_out[l].float().cpu(), cls_ref[l]) < REL_TOL, 'cls %d' % l
+    assert rel_l2(box_out[l].float().cpu(), box_ref[l]) < REL_TOL, 'box %d' % l
+
+
+def _assert_within_format_error(c, a, w, x, eng, cls_out, box_out, factor=1.5, slack=1e-4):
+  """Every block / BiFPN / head tensor of the engine within `factor` x the error that fp16 storage
+  and fp16 GEMM weights mandate for THIS network, weights and input (tests/precision_model.py:
+  the fp32 oracle with the same rounding sites, no kernel involved) + `slack`.  Returns the worst
+  (device error, model error) pair per tensor group."""
+  m = pm.DeviceModel(c, a, w, x)
+  worst = {}
+  def check(group, what, got, model_err, ref):
+    dev = rel_l2(got, ref)
+    assert dev < pm.bar(model_err, factor, slack), '%s: device %.3g, format model %.3g' % (what, dev, model_err)
+    if dev > worst.get(group, (0.0, 0.0))[0]:
+      worst[group] = (dev, model_err)
+  for b in a.blocks:
+    got = eng.buffers[b.name + '/out'].float().cpu().permute(0, 3, 1, 2)
+    check('blocks', b.name, got, model_err=m.endpoint_error(b.name), ref=m.ref.endpoints[b.name])
+  for l in a.levels:
+    got = eng.fpn_feats[l].float().cpu().permute(0, 3, 1, 2)
+    check('fpn', 'fpn %d' % l, got, model_err=m.endpoint_error('fpn_%d' % l), ref=m.ref.endpoints['fpn_%d' % l])
+    check('cls', 'cls %d' % l, cls_out[l].float().cpu(), model_err=m.cls_error(l), ref=m.cls_ref[l])
+    check('box', 'box %d' % l, box_out[l].float().cpu(), model_err=m.box_error(l), ref=m.box_ref[l])
+  return worst
+
+
+def test_network_parity_d7x_reduced_vs_format_model():
+  """BASELINE config 5's model (B7 backbone: 55 MBConv blocks, levels 3-8, F = 384, 8 'sum'
+  cells) at 256 x 256.  On seeded random weights an fp16-STORAGE design cannot meet 1e-3 here:
+  the fp32 oracle itself, with nothing but the engine's rounding sites applied (fp16 activations
+  in HBM, BN folded into fp16 GEMM weights; fp32 arithmetic), is 1.5e-3 off on the last block and
+  2.3e-3 on a box output -- a random walk over ~400 rounding sites.  The
+  kernels must add nothing to that: every tensor within 1.5x the format model + 1e-4."""
+  c, a, w, x = _setup('efficientdet-d7x', 256, 1)
+  eng = _engine(c, w, 1, use_cuda_graph=False)
+  cls_out, box_out = eng.forward(torch.from_numpy(x))
+  torch.cuda.synchronize()
+  worst = _assert_within_format_error(c, a, w, x, eng, cls_out, box_out)
+  assert worst['blocks'][0] < 2.5e-3 and worst['box'][0] < 3.5e-3   # absolute regression guard
 
 
 def test_network_parity_lite3():
   """A lite model end to end: relu6, no SE, `sum` fusion, and the fix_head_stem case where the
   first block is built on the stem's 32 channels although its block args say 40.
-  With RANDOM weights this relu6 / un-normalised-sum network is badly conditioned: the oracle's
-  own fp16-STORAGE model (fp32 arithmetic, activations rounded to fp16 between layers) is already
-  1e-3 off at block 5 and 1e-2 off on the box outputs.  The bar is therefore relative to that
-  model: every tensor within 2x the storage-model error + 5e-4."""
+  With RANDOM weights this relu6 / un-normalised-sum network is badly conditioned: the format
+  model (tests/precision_model.py) is already 1e-3 off at block 5 and 1e-2 off on the box
+  outputs, so the bar is relative to it: every tensor within 1.5x the model + 1e-4, and the first
+  blocks inside the absolute 1e-3."""
   c, a, w, x = _setup('efficientdet-lite3', 128, 1, seed=5)
   assert a.blocks[0].input_filters == 32 and a.blocks[0].mid_filters == 32
-  orc = eo.Oracle(c, w, torch.float32)
-  cls_ref, box_ref = orc(x)
-  o16 = eo.Oracle(c, w, torch.float32, store=eo.fp16_store)
-  cls_16, box_16 = o16(x)
   eng = _engine(c, w, 1, use_cuda_graph=False)
   cls_out, box_out = eng.forward(torch.from_numpy(x))
   torch.cuda.synchronize()
-  bar = lambda model, ref: 2.0 * rel_l2(model, ref) + 5e-4
-  for b in a.blocks:
-    got = eng.buffers[b.name + '/out'].float().cpu().permute(0, 3, 1, 2)
-    assert rel_l2(got, orc.endpoints[b.name]) < bar(o16.endpoints[b.name], orc.endpoints[b.name]), b.name
-  for l in a.levels:
-    assert rel_l2(cls_out[l].float().cpu(), cls_ref[l]) < bar(cls_16[l], cls_ref[l]), 'cls %d' % l
-    assert rel_l2(box_out[l].float().cpu(), box_ref[l]) < bar(box_16[l], box_ref[l]), 'box %d' % l
+  _assert_within_format_error(c, a, w, x, eng, cls_out, box_out)
+  orc = eo.Oracle(c, w, torch.float32)
+  orc(x)
   for b in a.blocks[:2]:   # the first blocks are still inside the absolute bar
     got = eng.buffers[b.name + '/out'].float().cpu().permute(0, 3, 1, 2)
     assert rel_l2(got, orc.endpoints[b.name]) < REL_TOL
@@ -153,25 +177,34 @@ def test_network_parity_d1_relu6():
     assert rel_l2(box_out[l].float().cpu(), box_ref[l]) < REL_TOL
 
 
-@pytest.mark.parametrize('over', [dict(fpn_weight_method='sum'),
-                                  dict(fpn_weight_method='sum', act_type='relu6')])
-def test_network_parity_sum_fusion(over):
-  """Un-normalised 'sum' fusion (the D6/D7/D7x and lite setting).  With RANDOM weights nothing
-  keeps the BiFPN activations from growing cell after cell, and the box-regression outputs come
-  out of cancellation between large terms: the oracle's own fp16-STORAGE model (activations
-  rounded to fp16 between kernels, everything else fp32) already costs 0.8-1.2e-3 relative on
-  the box outputs, and fp16 weights add to it.  Measured on the device: class outputs <= 5e-4,
-  box outputs ~2.1e-3.  So this configuration is held to 1e-3 on the class outputs and 2.5e-3 on
-  the box outputs, and is listed as an open item in DESIGN.md (real checkpoints, whose BiFPN
-  activations are trained to stay O(1), cannot be loaded offline)."""
-  c, a, w, x = _setup('efficientdet-d1', 128, 1, seed=3, **over)
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_network_parity_sum_fusion(seed):
+  """Un-normalised 'sum' fusion (the D6 / D7 / D7x and lite setting) at the 1e-3 bar on three
+  independent draws of weights and input."""
+  c, a, w, x = _setup('efficientdet-d1', 128, 1, seed=seed, fpn_weight_method='sum')
   cls32, box32 = eo.Oracle(c, w, torch.float32)(x)
   eng = _engine(c, w, 1, use_cuda_graph=False)
   cls_out, box_out = eng.forward(torch.from_numpy(x))
   torch.cuda.synchronize()
   for l in a.levels:
     assert rel_l2(cls_out[l].float().cpu(), cls32[l]) < REL_TOL
-    assert rel_l2(box_out[l].float().cpu(), box32[l]) < 2.5e-3
+    assert rel_l2(box_out[l].float().cpu(), box32[l]) < REL_TOL
+
+
+@pytest.mark.parametrize('over', [dict(fpn_weight_method='sum'),
+                                  dict(fpn_weight_method='sum', act_type='relu6')])
+def test_network_parity_sum_fusion_ill_conditioned_draw(over):
+  """Seed 3 is a draw on which nothing keeps the un-normalised BiFPN activations from growing and
+  the box-regression outputs come out of cancellation between large terms: the format model
+  (fp32 oracle + the engine's rounding sites, tests/precision_model.py) is itself 1.1e-3 (swish) /
+  1.4e-3 (relu6) off on a box output.  Class outputs stay inside 1e-3; every tensor must be
+  within 1.5x the format model + 1e-4."""
+  c, a, w, x = _setup('efficientdet-d1', 128, 1, seed=3, **over)
+  eng = _engine(c, w, 1, use_cuda_graph=False)
+  cls_out, box_out = eng.forward(torch.from_numpy(x))
+  torch.cuda.synchronize()
+  worst = _assert_within_format_error(c, a, w, x, eng, cls_out, box_out)
+  assert worst['cls'][0] < REL_TOL
 
 
 def test_detect_matches_oracle_postprocess_and_graph_replay():

@@ -59,7 +59,7 @@ def test_cuda_depthwise_same_padding_direction(k, s, size, pad_before):
   c = 8
   x = torch.ones(1, size, size, c, dtype=torch.float16, device=DEV)
   taps = torch.arange(k * k, dtype=torch.float32).reshape(k, k) + 1.0
-  w = taps.reshape(k * k, 1).expand(k * k, c).contiguous().half().to(DEV)
+  w = taps.reshape(k * k, 1).expand(k * k, c).contiguous().to(DEV)   # fp32 taps
   n_out = -(-size // s)
   out = torch.empty(1, n_out, n_out, c, dtype=torch.float16, device=DEV)
   ops.depthwise_conv(x, out, w, None, utils.ACT_NONE, k, s)
@@ -97,7 +97,7 @@ def test_cuda_fuse_nearest_index_rule(n_in, n_out, expect):
   ops = _ops()
   c = 8
   src = torch.arange(n_in, dtype=torch.float32).view(1, n_in, 1, 1).expand(1, n_in, n_in, c).contiguous().half()
-  dwk = torch.zeros(9, c, dtype=torch.float16)
+  dwk = torch.zeros(9, c, dtype=torch.float32)
   dwk[4] = 1.0
   out = torch.empty(1, n_out, n_out, c, dtype=torch.float16, device=DEV)
   ops.fuse_dw([(src.to(DEV), ops.RS_UP, None, 1.0)], dwk.to(DEV), out, utils.ACT_NONE)
