@@ -15,14 +15,32 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static std::atomic<int> g_opt_dw_impl{0};
-int option_dw_impl() { return g_opt_dw_impl.load(std::memory_order_relaxed); }
-static std::atomic<int> g_opt_stem_impl{0};
-int option_stem_impl() { return g_opt_stem_impl.load(std::memory_order_relaxed); }
-static std::atomic<int> g_opt_sepconv_impl{0};
-int option_sepconv_impl() { return g_opt_sepconv_impl.load(std::memory_order_relaxed); }
-static std::atomic<int> g_opt_pw_teams{0};
-int option_pw_teams() { return g_opt_pw_teams.load(std::memory_order_relaxed); }
+// Library options (edet_set_option): one table, looked up by name.
+struct Option {
+  const char* name;
+  int lo, hi;                  // accepted range (further restricted by `allowed` below)
+  std::atomic<int> value;
+};
+static Option g_options[] = {
+    {"dw_impl", 0, 2, {0}},          // 0 auto (tiled kernel where eligible), 1 register kernel only
+    {"stem_impl", 0, 1, {0}},        // 0 tensor-core stem, 1 CUDA-core stem
+    {"sepconv_impl", 0, 1, {0}},     // 0 TMA-staged input for c <= 64, 1 loads from global
+    {"pw_teams", 0, 3, {0}},         // 0 auto, 2 / 3 epilogue teams in pointwise_tc
+    {"pw_smem_kb", 0, 113, {0}},     // 0 auto, else shared-memory budget of a pointwise_tc CTA
+    {"persist_slack", 0, 148, {0}},  // CTAs a persistent kernel leaves out of its 2-per-SM grid
+};
+static Option* find_option(const char* name) {
+  for (Option& o : g_options)
+    if (strcmp(name, o.name) == 0) return &o;
+  return nullptr;
+}
+static int option_value(int idx) { return g_options[idx].value.load(std::memory_order_relaxed); }
+int option_dw_impl() { return option_value(0); }
+int option_stem_impl() { return option_value(1); }
+int option_sepconv_impl() { return option_value(2); }
+int option_pw_teams() { return option_value(3); }
+int option_pw_smem_kb() { return option_value(4); }
+int option_persist_slack() { return option_value(5); }
 
 int current_device() {
   int dev = -1;
@@ -77,50 +95,29 @@ extern "C" int edet_version(void) { return 200; }
 extern "C" int edet_set_option(const char* name, int value) {
   using namespace edet;
   EDET_CHECK_ARG(name != nullptr, "set_option: null name");
-  if (strcmp(name, "dw_impl") == 0) {
-    EDET_CHECK_ARG(value >= 0 && value <= 2, "set_option: dw_impl must be 0, 1 or 2");
-    g_opt_dw_impl.store(value);
-    return EDET_OK;
+  Option* o = find_option(name);
+  if (o == nullptr) {
+    set_error("set_option: unknown option '%s'", name);
+    return EDET_ERR_INVALID;
   }
-  if (strcmp(name, "sepconv_impl") == 0) {
-    EDET_CHECK_ARG(value == 0 || value == 1, "set_option: sepconv_impl must be 0 or 1");
-    g_opt_sepconv_impl.store(value);
-    return EDET_OK;
-  }
-  if (strcmp(name, "stem_impl") == 0) {
-    EDET_CHECK_ARG(value == 0 || value == 1, "set_option: stem_impl must be 0 or 1");
-    g_opt_stem_impl.store(value);
-    return EDET_OK;
-  }
-  if (strcmp(name, "pw_teams") == 0) {
-    EDET_CHECK_ARG(value == 0 || value == 2 || value == 3, "set_option: pw_teams must be 0, 2 or 3");
-    g_opt_pw_teams.store(value);
-    return EDET_OK;
-  }
-  set_error("set_option: unknown option '%s'", name);
-  return EDET_ERR_INVALID;
+  EDET_CHECK_ARG(value >= o->lo && value <= o->hi, "set_option: %s must be in %d..%d (got %d)", name,
+                 o->lo, o->hi, value);
+  EDET_CHECK_ARG(strcmp(name, "pw_teams") != 0 || value != 1, "set_option: pw_teams must be 0, 2 or 3");
+  EDET_CHECK_ARG(strcmp(name, "pw_smem_kb") != 0 || value == 0 || value >= 64,
+                 "set_option: pw_smem_kb must be 0 or 64..113");
+  o->value.store(value, std::memory_order_relaxed);
+  return EDET_OK;
 }
 extern "C" int edet_get_option(const char* name, int* value) {
   using namespace edet;
   EDET_CHECK_ARG(name != nullptr && value != nullptr, "get_option: null pointer");
-  if (strcmp(name, "dw_impl") == 0) {
-    *value = option_dw_impl();
-    return EDET_OK;
+  Option* o = find_option(name);
+  if (o == nullptr) {
+    set_error("get_option: unknown option '%s'", name);
+    return EDET_ERR_INVALID;
   }
-  if (strcmp(name, "sepconv_impl") == 0) {
-    *value = option_sepconv_impl();
-    return EDET_OK;
-  }
-  if (strcmp(name, "stem_impl") == 0) {
-    *value = option_stem_impl();
-    return EDET_OK;
-  }
-  if (strcmp(name, "pw_teams") == 0) {
-    *value = option_pw_teams();
-    return EDET_OK;
-  }
-  set_error("get_option: unknown option '%s'", name);
-  return EDET_ERR_INVALID;
+  *value = o->value.load(std::memory_order_relaxed);
+  return EDET_OK;
 }
 extern "C" const char* edet_last_error(void) { return edet::g_err; }
 extern "C" int edet_device_info(int* sm_count, int* cc) {

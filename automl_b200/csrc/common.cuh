@@ -176,6 +176,8 @@ int option_dw_impl();   // 0 auto (tiled kernel where eligible), 1 register kern
 int option_stem_impl(); // 0 auto (tensor-core stem), 1 CUDA-core stem kernel
 int option_sepconv_impl();  // 0 auto (TMA-staged input for c <= 64), 1 loads straight from global
 int option_pw_teams();  // 0 auto, 2 / 3 = force that many epilogue teams in pointwise_tc
+int option_pw_smem_kb();     // 0 auto, else the shared-memory budget (KiB) of a pointwise_tc CTA
+int option_persist_slack();  // CTAs a persistent kernel leaves out of its two-per-SM grid (default 0)
 constexpr int kMaxDevices = 64;
 int current_device();                 // ordinal of the current device, -1 (+ error text) on failure
 int device_sm_count();                // multiprocessor count of the current device, 0 on failure

@@ -294,7 +294,9 @@ static int run_ks(const __half* in, __half* out, const float* w, const float* bi
   if (int rc = make_map4(&mx, in, c, wd, h, n, kCB, C::TIW, C::TIH, /*swizzle=*/false)) return rc;
   const int sms = device_sm_count();
   if (!sms) return EDET_ERR_CUDA;
-  const int grid = p.total_units < 2 * sms ? p.total_units : 2 * sms;
+  int grid = 2 * sms - option_persist_slack();
+  if (grid < sms) grid = sms;
+  if (p.total_units < grid) grid = p.total_units;
   return launch_kernel<K, S>(mx, p, grid, act, stream);
 }
 

@@ -42,6 +42,7 @@ constexpr int kMaxStages = 8;
 constexpr int kRing = 4;          // tile-index ring entries (power of two)
 constexpr int kMaxAccum = 4;      // TMEM accumulator stages (thin N tiles)
 constexpr int kSmemLimit = 113 * 1024;                    // two CTAs per SM share the 227 KiB
+constexpr int kSmemCoResident = 99 * 1024;               // one CTA next to an nms_v5_fast CTA
 
 struct Params {
   int batch, rows, k, nout, nout_pad8;
@@ -528,23 +529,37 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   // one slab, then to 32-wide k-blocks, so that the TMA ring stays >= 3 deep (>= 2 at worst).
   const int ctrl = 2 * 256 * 4 + (2 * kMaxStages + 2 * kMaxAccum + 2 * kRing) * 8 + 16 + 4 * kRing;
   int best_stages = 0, fixed = 0, stage_bytes = 0;
-  for (int attempt = 0; attempt < 4 && best_stages < 3; ++attempt) {
-    const int bk = k <= 16 ? 16 : (k <= 32 ? 32 : (attempt >= 2 ? 32 : 64));
-    const int slabs = (attempt & 1) ? 1 : 2;
-    const int a_bytes = BLOCK_M * bk * 2;
-    const int b_bytes = ((p.block_n * bk * 2 + 1023) / 1024) * 1024;
-    const int fx = slabs * epi_warps * slab_bytes + ctrl;
-    int st = (kSmemLimit - 1024 - fx) / (a_bytes + b_bytes);
-    if (st > kMaxStages) st = kMaxStages;
-    if (st > best_stages) {
-      best_stages = st;
-      p.block_k = bk;
-      p.slabs_per_warp = slabs;
-      p.a_stage_bytes = a_bytes;
-      p.b_stage_bytes = b_bytes;
-      fixed = fx;
-      stage_bytes = a_bytes + b_bytes;
+  auto plan = [&](int limit) {
+    best_stages = 0;
+    for (int attempt = 0; attempt < 4 && best_stages < 3; ++attempt) {
+      const int bk = k <= 16 ? 16 : (k <= 32 ? 32 : (attempt >= 2 ? 32 : 64));
+      const int slabs = (attempt & 1) ? 1 : 2;
+      const int a_bytes = BLOCK_M * bk * 2;
+      const int b_bytes = ((p.block_n * bk * 2 + 1023) / 1024) * 1024;
+      const int fx = slabs * epi_warps * slab_bytes + ctrl;
+      int st = (limit - 1024 - fx) / (a_bytes + b_bytes);
+      if (st > kMaxStages) st = kMaxStages;
+      if (st > best_stages) {
+        best_stages = st;
+        p.block_k = bk;
+        p.slabs_per_warp = slabs;
+        p.a_stage_bytes = a_bytes;
+        p.b_stage_bytes = b_bytes;
+        fixed = fx;
+        stage_bytes = a_bytes + b_bytes;
+      }
     }
+  };
+  // Shared-memory budget.  The NMS of the previous batch (one 126 KiB CTA per image, own stream)
+  // runs under the first layers of the next network: with 99 KiB a pointwise CTA fits next to it
+  // (99 + 126 + 2 KiB <= 228 KiB), with 113 KiB those SMs stay empty.  So 99 KiB wherever that
+  // still gives a ring of >= 4 stages (every thin-K layer), the full half SM otherwise.
+  const int opt_kb = option_pw_smem_kb();
+  if (opt_kb) {
+    plan(opt_kb * 1024);
+  } else {
+    plan(kSmemCoResident);
+    if (best_stages < 4) plan(kSmemLimit);
   }
   EDET_CHECK_ARG(best_stages >= 2, "pointwise_tc: block_n %d leaves <2 pipeline stages", p.block_n);
   p.num_stages = best_stages;
@@ -568,7 +583,9 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
 
   const int sm_count = device_sm_count();
   if (!sm_count) return EDET_ERR_CUDA;
-  const int grid = p.total_tiles < 2 * sm_count ? p.total_tiles : 2 * sm_count;
+  int grid = 2 * sm_count - option_persist_slack();
+  if (grid < sm_count) grid = sm_count;
+  if (p.total_tiles < grid) grid = p.total_tiles;
   const bool has_res = residual != nullptr;
 
 #define EDET_PW_CASE(A)                                                                       \

@@ -58,7 +58,7 @@ class Engine(object):
 
   def __init__(self, config, weights, batch_size, device='cuda:0', pw_impl=ops.PW_TCGEN05,
                use_cuda_graph=True, image_id_base=0, fuse_mbconv_front=False,
-               fuse_sepconv=True, fuse_sepconv_nodes=False):
+               fuse_sepconv=True, fuse_sepconv_nodes=False, pipeline=True):
     if not torch.cuda.is_available():
       raise RuntimeError('automl_b200.Engine needs a CUDA device; there is no CPU fallback')
     self.config = config
@@ -73,8 +73,15 @@ class Engine(object):
     self.fuse_mbconv_front = fuse_mbconv_front
     self.fuse_sepconv = fuse_sepconv              # head tower layers: dw + pw in one kernel
     self.fuse_sepconv_nodes = fuse_sepconv_nodes  # BiFPN nodes (measured slower than the pair)
+    # pipeline: run(postprocess=True) overlaps the backbone of step i+1 (main stream) with the
+    # feature network + heads + pre-NMS of step i (head stream) and the NMS of step i (NMS stream)
+    if os.environ.get('EDET_PIPELINE'):        # A/B switch for scripts / bench runs
+      pipeline = os.environ['EDET_PIPELINE'] != '0'
+    self.pipeline = pipeline
     self.act = utils.activation_code(a.act_type)
     self._graph = None
+    self._bb_split = None
+    self._cell0_end = None
     self._ops = []          # (name, callable)
     self.op_info = []       # parallel to _ops: kind / algorithmic bytes / flops
     self._branch = None
@@ -220,6 +227,9 @@ class Engine(object):
       proj_b = self._dev(sh, f32)
       y = self._buf(b.name + '/out', (n, ho, wo, b.output_filters))
       res = x_in if b.has_skip else None
+      if b.reduction and b.reduction >= a.config.min_level and self._bb_split is None:
+        # first op that writes a backbone feature the feature network reads (see run())
+        self._bb_split = len(self._ops) + (1 if b.se_filters else 0)
       if b.se_filters:
         w1 = self._dev(np.asarray(w[scope + '/se/conv2d/kernel'], np.float64)[0, 0].T, f32)   # [se,C]
         b1 = self._dev(w[scope + '/se/conv2d/bias'], f32)
@@ -243,6 +253,10 @@ class Engine(object):
       cur, cur_hw = y, (ho, wo)
       if b.reduction:
         feats[b.reduction] = y
+
+    self.num_backbone_ops = len(self._ops)
+    if self._bb_split is None:
+      self._bb_split = self.num_backbone_ops
 
     # -- feature network --------------------------------------------------------------------
     F = a.fpn_filters
@@ -358,6 +372,8 @@ class Engine(object):
           self._pw(node.scope + '/pw', tmp, pw_wt, pw_b, out, utils.ACT_NONE)
         cell_feats.append(out)
       pyramid = [cell_feats[cell['out_index'][l]] for l in a.levels]
+      if ci == 0:
+        self._cell0_end = len(self._ops)   # nothing after this launch reads a backbone feature
     self.fpn_feats = dict(zip(a.levels, pyramid))
 
     # -- heads ----------------------------------------------------------------------------------
@@ -461,7 +477,15 @@ class Engine(object):
           ps['detections'], ps['sel_index'], ps['valid'], ps['work']))
     self._cur = 0
     self._step = 0
-    self._nms_stream = torch.cuda.Stream(device=self.device)
+    # head / NMS stages run at high priority: their short, dependent kernels should take the SM
+    # slots that free up between the persistent CTAs of the (next) backbone
+    self._head_priority = -1 if os.environ.get('EDET_HEAD_PRIO', '1') != '0' else 0
+    self._nms_stream = torch.cuda.Stream(device=self.device, priority=self._head_priority)
+    self._head_stream = torch.cuda.Stream(device=self.device, priority=self._head_priority)
+    self._head_capture_stream = torch.cuda.Stream(device=self.device, priority=self._head_priority)
+    self._ev_bb = torch.cuda.Event()
+    self._ev_head = torch.cuda.Event()
+    self._head_pending = False
     self._ev_pre = [torch.cuda.Event() for _ in range(2)]
     self._ev_nms = [torch.cuda.Event() for _ in range(2)]
     self._nms_pending = [False, False]
@@ -472,13 +496,16 @@ class Engine(object):
     self.launches_per_forward = sum(i['kernels'] for i in self.op_info)
 
   # ---- execution ------------------------------------------------------------------------------
-  def _run_ops(self, upto=None, parallel_branches=True):
-    """Runs the launch list on the current stream; ops tagged with a branch run on side streams
-    forked from / joined back into it (parallel graph branches when captured)."""
-    ops_list = self._ops if upto is None else self._ops[:upto]
+  def _run_ops(self, upto=None, parallel_branches=True, start=0, priority=0):
+    """Runs ops [start, upto) of the launch list on the current stream; ops tagged with a branch
+    run on side streams forked from / joined back into it (parallel graph branches when
+    captured).  priority: CUDA priority of the side streams (the head half of a pipelined step
+    runs at high priority so that its short kernels are not queued behind the next backbone)."""
+    upto = len(self._ops) if upto is None else upto
     main = torch.cuda.current_stream(self.device)
     open_branches = {}
-    for i, (_, fn) in enumerate(ops_list):
+    for i in range(start, upto):
+      fn = self._ops[i][1]
       br = self.op_info[i]['branch'] if parallel_branches else None
       if br is None:
         # join every open branch except the detached ('~...') ones this op does not consume
@@ -490,9 +517,10 @@ class Engine(object):
         continue
       st = open_branches.get(br)
       if st is None:
-        st = self._branch_streams.get(br)
+        st = self._branch_streams.get((br, priority))
         if st is None:
-          st = self._branch_streams[br] = torch.cuda.Stream(device=self.device)
+          st = self._branch_streams[(br, priority)] = torch.cuda.Stream(device=self.device,
+                                                                        priority=priority)
         st.wait_stream(main)                   # fork
         open_branches[br] = st
       with torch.cuda.stream(st):
@@ -532,14 +560,15 @@ class Engine(object):
   def valid(self):
     return self._post[self._cur]['valid']
 
-  def _graph_for(self, key, fn):
+  def _graph_for(self, key, fn, capture_stream=None, warm=True):
     if self._graph is None:
       self._graph = {}
     if key not in self._graph:
-      fn()                                   # warm-up outside capture (kernel attributes, modules)
+      if warm:
+        fn()                                 # warm-up outside capture (kernel attributes, modules)
       torch.cuda.synchronize(self.device)
       g = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(g):
+      with torch.cuda.graph(g, stream=capture_stream):
         fn()
       self._graph[key] = g
     return self._graph[key]
@@ -555,6 +584,8 @@ class Engine(object):
     """
     net_upto = self.num_network_ops
     if not postprocess:
+      if self._head_pending:   # a pipelined step may still be reading / writing the head buffers
+        torch.cuda.current_stream(self.device).wait_event(self._ev_pre[self._cur])
       if self.use_cuda_graph:
         self._graph_for('net', lambda: self._run_ops(net_upto)).replay()
       else:
@@ -563,16 +594,19 @@ class Engine(object):
     sidx = self._step % 2
     self._step += 1
     main = torch.cuda.current_stream(self.device)
-    if self._nms_pending[sidx]:
-      main.wait_event(self._ev_nms[sidx])      # the NMS that last read this buffer set is done
-    def net_and_pre():
-      self._run_ops(net_upto)
-      self._pre_ops[sidx]()
-    if self.use_cuda_graph:
-      self._graph_for(('net+pre', sidx), net_and_pre).replay()
+    if self.pipeline:
+      self._run_pipelined(sidx, main)
     else:
-      net_and_pre()
-    self._ev_pre[sidx].record(main)
+      if self._nms_pending[sidx]:
+        main.wait_event(self._ev_nms[sidx])      # the NMS that last read this buffer set is done
+      def net_and_pre():
+        self._run_ops(net_upto)
+        self._pre_ops[sidx]()
+      if self.use_cuda_graph:
+        self._graph_for(('net+pre', sidx), net_and_pre).replay()
+      else:
+        net_and_pre()
+      self._ev_pre[sidx].record(main)
     with torch.cuda.stream(self._nms_stream):
       self._nms_stream.wait_event(self._ev_pre[sidx])
       if self.use_cuda_graph:
@@ -584,6 +618,57 @@ class Engine(object):
       self._ev_nms[sidx].record(self._nms_stream)
     self._nms_pending[sidx] = True
     self._cur = sidx
+
+  def _run_pipelined(self, sidx, main):
+    """One step as three overlapping stages (records self._ev_pre[sidx] for the NMS stage):
+
+      main stream : stem + MBConv blocks of THIS step (throughput bound: the large maps)
+      head stream : feature network + heads + pre-NMS (latency bound: ~100 short dependent
+                    launches on small maps) -- runs under the backbone of the NEXT step
+      NMS stream  : NMS-V5 (+ after_nms hook), as before
+
+    The only tensors the two halves share are the backbone features P3..P5.  No second copy of
+    them is needed: the backbone is cut in two graphs at the first launch that writes one of them
+    (blocks_4/project in D0, 1.6 ms into the backbone) and the main stream waits there for the
+    first BiFPN cell of the previous step -- the only reader -- which by then has long finished."""
+    split, nb, net_upto = self._bb_split, self.num_backbone_ops, self.num_network_ops
+    hs = self._head_stream
+    c0 = self._cell0_end if self._cell0_end is not None else nb
+
+    if self.use_cuda_graph and (self._graph is None or ('heads+pre', sidx) not in self._graph):
+      # One eager forward (kernel attributes, module loading), then the captures -- which execute
+      # nothing -- so the partial graphs are never run out of order: bb2 alone would add the SE
+      # sums of its first block onto a stale accumulator.
+      if self._graph is None or 'bb1' not in self._graph:
+        self._run_ops(net_upto)
+        self._pre_ops[0]()
+        self._pre_ops[1]()
+
+    def replay(key, fn, capture_stream=None):
+      if self.use_cuda_graph:
+        self._graph_for(key, fn, capture_stream, warm=False).replay()
+      else:
+        fn()
+
+    replay('bb1', lambda: self._run_ops(split))
+    if self._head_pending:
+      main.wait_event(self._ev_head)           # previous step's head stage has read P3..P5
+    replay('bb2', lambda: self._run_ops(nb, start=split))
+    self._ev_bb.record(main)
+    with torch.cuda.stream(hs):
+      hs.wait_event(self._ev_bb)
+      if self._nms_pending[sidx]:
+        hs.wait_event(self._ev_nms[sidx])      # the NMS that last read this buffer set is done
+      # first BiFPN cell (+ extra levels): the only reader of P3..P5
+      replay('cell0', lambda: self._run_ops(c0, start=nb, priority=self._head_priority),
+             self._head_capture_stream)
+      self._ev_head.record(hs)
+      def heads_and_pre():
+        self._run_ops(net_upto, start=c0, priority=self._head_priority)
+        self._pre_ops[sidx]()
+      replay(('heads+pre', sidx), heads_and_pre, self._head_capture_stream)
+      self._ev_pre[sidx].record(hs)
+    self._head_pending = True
 
   def wait_detections(self):
     """Makes the current stream wait for the NMS (and after_nms hook) of the latest step."""
