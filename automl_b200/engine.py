@@ -58,7 +58,7 @@ class Engine(object):
 
   def __init__(self, config, weights, batch_size, device='cuda:0', pw_impl=ops.PW_TCGEN05,
                use_cuda_graph=True, image_id_base=0, fuse_mbconv_front=False,
-               fuse_sepconv=True, fuse_sepconv_nodes=False, pipeline=True):
+               fuse_sepconv=True, fuse_sepconv_nodes=False, pipeline=True, defer_heads=False):
     if not torch.cuda.is_available():
       raise RuntimeError('automl_b200.Engine needs a CUDA device; there is no CPU fallback')
     self.config = config
@@ -78,6 +78,10 @@ class Engine(object):
     if os.environ.get('EDET_PIPELINE'):        # A/B switch for scripts / bench runs
       pipeline = os.environ['EDET_PIPELINE'] != '0'
     self.pipeline = pipeline
+    if os.environ.get('EDET_DEFER_HEADS'):
+      defer_heads = os.environ['EDET_DEFER_HEADS'] != '0'
+    self.defer_heads = bool(defer_heads and pipeline)   # see _run_pipelined
+    self._deferred = None
     self.act = utils.activation_code(a.act_type)
     self._graph = None
     self._bb_split = None
@@ -257,6 +261,16 @@ class Engine(object):
     self.num_backbone_ops = len(self._ops)
     if self._bb_split is None:
       self._bb_split = self.num_backbone_ops
+    if self.defer_heads:
+      # the held-back head stage reads copies of P3..P5 (see _run_pipelined); torch's copy kernel
+      for level in sorted(feats):
+        if level >= a.config.min_level:
+          src = feats[level]
+          dst = self._buf('P%d_copy' % level, tuple(src.shape))
+          self._add('feat_copy/P%d' % level, lambda src=src, dst=dst: dst.copy_(src),
+                    kind='memcpy', nbytes=4 * src.numel(), kernels=0)
+          feats[level] = dst
+    self._heads_start = len(self._ops)
 
     # -- feature network --------------------------------------------------------------------
     F = a.fpn_filters
@@ -477,13 +491,22 @@ class Engine(object):
           ps['detections'], ps['sel_index'], ps['valid'], ps['work']))
     self._cur = 0
     self._step = 0
-    # head / NMS stages run at high priority: their short, dependent kernels should take the SM
-    # slots that free up between the persistent CTAs of the (next) backbone
-    self._head_priority = -1 if os.environ.get('EDET_HEAD_PRIO', '1') != '0' else 0
-    self._nms_stream = torch.cuda.Stream(device=self.device, priority=self._head_priority)
+    # image scales of the steps in flight: the caller writes entry step % 4 before run(); the NMS
+    # stage copies it into its buffer set on the NMS stream (so staging step i+2 never races the
+    # NMS of step i, which uses the same set and may still be queued)
+    self._scales_ring = [self._buf('image_scales_ring%d' % i, (n,), f32) for i in range(4)]
+    for t in self._scales_ring:
+      t.fill_(1.0)
+    # Stream priorities of the head and NMS stages (A/B switches).  Measured on the D0 step: a
+    # high-priority head stage pushes whole waves of the next backbone out (4.04 ms), equal
+    # priorities let it fill the slots the backbone leaves (3.90 ms).
+    self._head_priority = -1 if os.environ.get('EDET_HEAD_PRIO', '0') != '0' else 0
+    self._nms_priority = -1 if os.environ.get('EDET_NMS_PRIO', '0') != '0' else 0
+    self._nms_stream = torch.cuda.Stream(device=self.device, priority=self._nms_priority)
     self._head_stream = torch.cuda.Stream(device=self.device, priority=self._head_priority)
     self._head_capture_stream = torch.cuda.Stream(device=self.device, priority=self._head_priority)
     self._ev_bb = torch.cuda.Event()
+    self._ev_early = torch.cuda.Event()
     self._ev_head = torch.cuda.Event()
     self._head_pending = False
     self._ev_pre = [torch.cuda.Event() for _ in range(2)]
@@ -533,7 +556,7 @@ class Engine(object):
     """float32 [N] image_scale_to_original of the NEXT run(postprocess=True): write it (on the
     current stream) before calling run() / detect().  One buffer per post-processing set, so
     staging step i+1 never races the NMS of step i."""
-    return self._post[self._step % 2]['image_scales']
+    return self._scales_ring[self._step % 4]
 
   # buffers of the most recent post-processed step
   @property
@@ -584,6 +607,7 @@ class Engine(object):
     """
     net_upto = self.num_network_ops
     if not postprocess:
+      self.flush()
       if self._head_pending:   # a pipelined step may still be reading / writing the head buffers
         torch.cuda.current_stream(self.device).wait_event(self._ev_pre[self._cur])
       if self.use_cuda_graph:
@@ -592,10 +616,11 @@ class Engine(object):
         self._run_ops(net_upto)
       return
     sidx = self._step % 2
+    ring = self._step % 4
     self._step += 1
     main = torch.cuda.current_stream(self.device)
     if self.pipeline:
-      self._run_pipelined(sidx, main)
+      self._run_pipelined(sidx, main, after_nms, ring)
     else:
       if self._nms_pending[sidx]:
         main.wait_event(self._ev_nms[sidx])      # the NMS that last read this buffer set is done
@@ -607,8 +632,13 @@ class Engine(object):
       else:
         net_and_pre()
       self._ev_pre[sidx].record(main)
+      self._enqueue_nms(sidx, after_nms, ring)
+    self._cur = sidx
+
+  def _enqueue_nms(self, sidx, after_nms, ring):
     with torch.cuda.stream(self._nms_stream):
       self._nms_stream.wait_event(self._ev_pre[sidx])
+      self._post[sidx]['image_scales'].copy_(self._scales_ring[ring], non_blocking=True)
       if self.use_cuda_graph:
         self._graph_for(('nms', sidx), self._nms_ops[sidx]).replay()
       else:
@@ -617,24 +647,33 @@ class Engine(object):
         after_nms(self._post[sidx]['detections'])
       self._ev_nms[sidx].record(self._nms_stream)
     self._nms_pending[sidx] = True
-    self._cur = sidx
 
-  def _run_pipelined(self, sidx, main):
-    """One step as three overlapping stages (records self._ev_pre[sidx] for the NMS stage):
+  def _replay(self, key, fn, capture_stream=None):
+    if self.use_cuda_graph:
+      self._graph_for(key, fn, capture_stream, warm=False).replay()
+    else:
+      fn()
+
+  def _run_pipelined(self, sidx, main, after_nms, ring):
+    """One step as three overlapping stages:
 
       main stream : stem + MBConv blocks of THIS step (throughput bound: the large maps)
-      head stream : feature network + heads + pre-NMS (latency bound: ~100 short dependent
-                    launches on small maps) -- runs under the backbone of the NEXT step
-      NMS stream  : NMS-V5 (+ after_nms hook), as before
+      head stream : feature network + heads + pre-NMS (~100 short dependent launches, mostly on
+                    small maps) -- runs under the backbone of the NEXT step
+      NMS stream  : NMS-V5 (+ after_nms hook)
 
-    The only tensors the two halves share are the backbone features P3..P5.  No second copy of
-    them is needed: the backbone is cut in two graphs at the first launch that writes one of them
-    (blocks_4/project in D0, 1.6 ms into the backbone) and the main stream waits there for the
-    first BiFPN cell of the previous step -- the only reader -- which by then has long finished."""
-    split, nb, net_upto = self._bb_split, self.num_backbone_ops, self.num_network_ops
-    hs = self._head_stream
-    c0 = self._cell0_end if self._cell0_end is not None else nb
-
+    The only tensors the two halves share are the backbone features P3..P5.
+    defer_heads=False: the head stage of step i is enqueued right away and overlaps the EARLY
+      backbone of step i+1.  No copy of P3..P5 is needed: the backbone is cut in two graphs at the
+      first launch that writes one of them (blocks_4/project in D0, 1.6 ms into the backbone) and
+      the main stream waits there for the first BiFPN cell of the previous step -- their only
+      reader -- which by then has long finished.
+    defer_heads=True: the head stage of step i is held back until step i+1 has been submitted and
+      starts when its early backbone is done, so that the ~100 short head launches overlap the
+      LATE, small-map backbone layers (blocks_5.. in D0) instead of the bandwidth-bound first
+      layers.  P3..P5 are then copied (35 MB in D0, ~12 us) at the end of the backbone, and the
+      head stage reads the copies.  flush() / wait_detections() submit a held-back head stage."""
+    split, nb, nbc, net_upto = self._bb_split, self.num_backbone_ops, self._heads_start, self.num_network_ops
     if self.use_cuda_graph and (self._graph is None or ('heads+pre', sidx) not in self._graph):
       # One eager forward (kernel attributes, module loading), then the captures -- which execute
       # nothing -- so the partial graphs are never run out of order: bb2 alone would add the SE
@@ -643,35 +682,58 @@ class Engine(object):
         self._run_ops(net_upto)
         self._pre_ops[0]()
         self._pre_ops[1]()
+    self._replay('bb1', lambda: self._run_ops(split))
+    if self.defer_heads:
+      self._ev_early.record(main)
+      self.flush(after=self._ev_early)          # head + NMS stages of the previous step
+      self._replay('bb2', lambda: self._run_ops(nb, start=split))
+      if self._head_pending:
+        main.wait_event(self._ev_head)          # first BiFPN cell of the previous step read the copies
+      self._replay('featcopy', lambda: self._run_ops(nbc, start=nb))
+      self._ev_bb.record(main)
+      self._deferred = (sidx, after_nms, ring)
+    else:
+      if self._head_pending:
+        main.wait_event(self._ev_head)          # previous step's first BiFPN cell has read P3..P5
+      self._replay('bb2', lambda: self._run_ops(nbc, start=split))
+      self._ev_bb.record(main)
+      self._enqueue_heads(sidx, None)
+      self._enqueue_nms(sidx, after_nms, ring)
 
-    def replay(key, fn, capture_stream=None):
-      if self.use_cuda_graph:
-        self._graph_for(key, fn, capture_stream, warm=False).replay()
-      else:
-        fn()
-
-    replay('bb1', lambda: self._run_ops(split))
-    if self._head_pending:
-      main.wait_event(self._ev_head)           # previous step's head stage has read P3..P5
-    replay('bb2', lambda: self._run_ops(nb, start=split))
-    self._ev_bb.record(main)
+  def _enqueue_heads(self, sidx, after):
+    nbc, net_upto = self._heads_start, self.num_network_ops
+    c0 = self._cell0_end if self._cell0_end is not None else nbc
+    hs = self._head_stream
     with torch.cuda.stream(hs):
       hs.wait_event(self._ev_bb)
+      if after is not None:
+        hs.wait_event(after)
       if self._nms_pending[sidx]:
         hs.wait_event(self._ev_nms[sidx])      # the NMS that last read this buffer set is done
-      # first BiFPN cell (+ extra levels): the only reader of P3..P5
-      replay('cell0', lambda: self._run_ops(c0, start=nb, priority=self._head_priority),
-             self._head_capture_stream)
+      # first BiFPN cell (+ extra levels): the only reader of P3..P5 (or of their copies)
+      self._replay('cell0', lambda: self._run_ops(c0, start=nbc, priority=self._head_priority),
+                   self._head_capture_stream)
       self._ev_head.record(hs)
       def heads_and_pre():
         self._run_ops(net_upto, start=c0, priority=self._head_priority)
         self._pre_ops[sidx]()
-      replay(('heads+pre', sidx), heads_and_pre, self._head_capture_stream)
+      self._replay(('heads+pre', sidx), heads_and_pre, self._head_capture_stream)
       self._ev_pre[sidx].record(hs)
     self._head_pending = True
 
+  def flush(self, after=None):
+    """Submits the head + NMS stages of the latest step if they are being held back
+    (defer_heads); `after`: an event they additionally wait for.  No-op otherwise."""
+    if self._deferred is not None:
+      sidx, after_nms, ring = self._deferred
+      self._deferred = None
+      with torch.cuda.device(self.device):
+        self._enqueue_heads(sidx, after)
+        self._enqueue_nms(sidx, after_nms, ring)
+
   def wait_detections(self):
     """Makes the current stream wait for the NMS (and after_nms hook) of the latest step."""
+    self.flush()
     torch.cuda.current_stream(self.device).wait_event(self._ev_nms[self._cur])
 
   def set_input(self, images):
@@ -713,6 +775,7 @@ class Engine(object):
 
   def nms_fallback_count(self):
     """Images of the last run that needed the full-queue NMS kernel (fast path not provable)."""
+    self.wait_detections()
     flags = self._post[self._cur]['work'][-4 * self.n:].view(torch.int32)
     return int(flags.sum().item())
 

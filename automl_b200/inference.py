@@ -106,6 +106,7 @@ class _Request(object):
 
   def _finish(self):
     if self._out is None:
+      self._slot['engine'].flush()        # a head / NMS stage the engine may still be holding back
       self._slot['ev_done'].synchronize()
       self._out = self._slot['host_det'].numpy().copy()
       if self._slot['pending'] is self:
@@ -113,6 +114,8 @@ class _Request(object):
     return self._out
 
   def done(self):
+    if self._out is None:
+      self._slot['engine'].flush()
     return self._out is not None or self._slot['ev_done'].query()
 
   def result(self):
@@ -123,6 +126,8 @@ class _Request(object):
 
 class ServingDriver(object):
   """A driver for serving single or batch images (reference inference.py:340)."""
+
+  MAX_IN_FLIGHT = 3   # submit(): requests whose results have not been collected yet
 
   def __init__(self, model_name, ckpt_path, batch_size=1, use_xla=False, min_score_thresh=None,
                max_boxes_to_draw=None, line_thickness=None, model_params=None, device='cuda:0',
@@ -181,9 +186,10 @@ class ServingDriver(object):
       world = 1
       if torch.distributed.is_available() and torch.distributed.is_initialized():
         world = torch.distributed.get_world_size()
-      # two in-flight requests per batch size: pinned host staging / result buffers, device raw
+      # MAX_IN_FLIGHT requests per batch size: pinned host staging / result buffers, device raw
       # buffers and the events that order their reuse
       self._slots[n] = [{
+          'engine': eng,
           'host_det': torch.empty(world * n, eng.max_output_size, 7).pin_memory(),
           'scales': torch.empty(n, dtype=torch.float32).pin_memory(),
           'gathered': (torch.empty(world * n, eng.max_output_size, 7, device=self.device)
@@ -191,7 +197,7 @@ class ServingDriver(object):
           'raw_host': None, 'raw_dev': None,
           'ev_h2d': torch.cuda.Event(), 'ev_raw_free': torch.cuda.Event(),
           'ev_done': torch.cuda.Event(), 'pending': None,
-      } for _ in range(2)]
+      } for _ in range(self.MAX_IN_FLIGHT)]
     return eng
 
   # ---- serving -------------------------------------------------------------------------------
@@ -239,10 +245,10 @@ class ServingDriver(object):
 
   def submit(self, image_arrays):
     """Enqueues one request and returns a handle; `handle.result()` blocks until its detections
-    are in host memory.  Up to two requests are in flight: the H2D copy and pre-process of
-    request i+1 and the NMS + D2H copy of request i-1 overlap the network of request i (copy
-    stream, main stream, the engine's NMS stream).  Submitting a third request first completes
-    the oldest one."""
+    are in host memory.  Up to MAX_IN_FLIGHT (3) requests are in flight: the H2D copy and
+    pre-process of request i+1, the backbone of request i, the feature network / heads of request
+    i-1 and the NMS + D2H copy of request i-1 / i-2 overlap (copy stream, main stream, the engine's
+    head and NMS streams).  Submitting one more request first completes the oldest one."""
     if getattr(self, '_engines', None) is None:
       self.build()
     n = len(image_arrays)
@@ -252,7 +258,7 @@ class ServingDriver(object):
       raise ValueError('empty request')
     with torch.cuda.device(self.device):
       eng = self._engine_for(n)
-      slot = self._slots[n][self._seq % 2]
+      slot = self._slots[n][self._seq % self.MAX_IN_FLIGHT]
       self._seq += 1
       if slot['pending'] is not None:
         slot['pending']._finish()          # its host buffer is about to be reused
@@ -278,15 +284,15 @@ class ServingDriver(object):
 
   def serve_stream(self, batches):
     """Generator over an iterable of requests: yields the detections of each, in order, keeping
-    two requests in flight."""
-    prev = None
+    MAX_IN_FLIGHT requests in flight."""
+    import collections  # pylint: disable=g-import-not-at-top
+    pending = collections.deque()
     for batch in batches:
-      cur = self.submit(batch)
-      if prev is not None:
-        yield prev.result()
-      prev = cur
-    if prev is not None:
-      yield prev.result()
+      pending.append(self.submit(batch))
+      if len(pending) >= self.MAX_IN_FLIGHT:
+        yield pending.popleft().result()
+    while pending:
+      yield pending.popleft().result()
 
   def serve_files(self, image_files):
     """image_files: list of encoded image bytes (jpeg/png)."""

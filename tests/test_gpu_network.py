@@ -268,26 +268,33 @@ def test_efficientdet_call_surface():
   assert cls_out[3].dtype == torch.float32
 
 
+@pytest.mark.parametrize('defer', [False, True])
 @pytest.mark.parametrize('graph', [True, False])
-def test_pipelined_steps_equal_sequential_steps(graph):
+def test_pipelined_steps_equal_sequential_steps(graph, defer):
   """Engine(pipeline=True) overlaps the backbone of step i+1 with the feature network / heads /
-  pre-NMS of step i and the NMS of step i (three streams, four partial graphs).  Six consecutive
-  steps on six different inputs, enqueued without any host synchronisation in between, must give
-  bit-identical detections and head outputs to the un-pipelined engine run one step at a time."""
+  pre-NMS of step i and the NMS of step i (three streams, partial graphs; defer_heads=True holds
+  the head stage of a step back until the next step's early backbone is done and reads copies of
+  P3..P5).  Six consecutive steps on six different inputs and image scales, enqueued without any
+  host synchronisation in between, must give bit-identical detections and head outputs to the
+  un-pipelined engine run one step at a time."""
   c, a, w, _ = _setup('efficientdet-d0', 128, 2, seed=11)
   rng = np.random.default_rng(12)
   xs = [torch.from_numpy(rng.uniform(-2, 2, size=(2, 128, 128, 3)).astype(np.float32)).cuda() for _ in range(6)]
+  scales = [torch.tensor([1.0 + 0.25 * i, 2.0 - 0.25 * i], device='cuda') for i in range(6)]
   seq = _engine(c, w, 2, use_cuda_graph=graph, pipeline=False)
   want, want_cls = [], []
-  for x in xs:
-    want.append(seq.detect(x).clone())
+  for x, sc in zip(xs, scales):
+    want.append(seq.detect(x, sc).clone())
     want_cls.append(seq.cls_out[a.levels[0]].clone())
   torch.cuda.synchronize()
-  pipe = _engine(c, w, 2, use_cuda_graph=graph, pipeline=True)
-  assert pipe.pipeline and 0 < pipe._bb_split < pipe.num_backbone_ops < pipe._cell0_end < pipe.num_network_ops  # pylint: disable=protected-access
+  assert not torch.equal(want[0][..., 1:5], want[1][..., 1:5])
+  pipe = _engine(c, w, 2, use_cuda_graph=graph, pipeline=True, defer_heads=defer)
+  assert pipe.pipeline and pipe.defer_heads == defer
+  assert 0 < pipe._bb_split < pipe.num_backbone_ops <= pipe._heads_start < pipe._cell0_end < pipe.num_network_ops  # pylint: disable=protected-access
   got = [torch.empty_like(want[0]) for _ in xs]
   for i, x in enumerate(xs):
     pipe.input.copy_(x, non_blocking=True)     # main stream: ordered after the previous stem
+    pipe.image_scales.copy_(scales[i], non_blocking=True)
     pipe.run(postprocess=True, after_nms=lambda det, i=i: got[i].copy_(det, non_blocking=True))
   pipe.wait_detections()
   torch.cuda.synchronize()
@@ -298,3 +305,5 @@ def test_pipelined_steps_equal_sequential_steps(graph):
   cls_out, _ = pipe.forward(xs[0])
   torch.cuda.synchronize()
   assert torch.equal(cls_out[a.levels[0]], want_cls[0][..., :cls_out[a.levels[0]].shape[-1]])
+  # detect() right after (a held-back head stage is flushed by wait_detections)
+  assert torch.equal(pipe.detect(xs[2], scales[2]), want[2])

@@ -105,8 +105,8 @@ def test_generate_detections_per_class_path():
 
 
 def test_pipelined_submit_equals_synchronous_serving():
-  """submit()/result() keeps two requests in flight (H2D + pre-process of request i+1 and NMS +
-  D2H of request i-1 overlap the network of request i): results must equal the synchronous
+  """submit()/result() keeps up to three requests in flight (H2D + pre-process of request i+1, the
+  head stage / NMS + D2H of request i-1 overlap the backbone of request i): results must equal the synchronous
   serve_images() of the same batches, in order, also when slots are reused."""
   from automl_b200 import inference
   rng = np.random.default_rng(2)
@@ -123,11 +123,13 @@ def test_pipelined_submit_equals_synchronous_serving():
   got.append(handles.pop(0).result())
   for g, e in zip(got, expect):
     np.testing.assert_array_equal(g, e)
-  # a third submit completes the oldest request by itself
-  h = [driver.submit(b) for b in batches[:3]]
+  # a submit beyond MAX_IN_FLIGHT completes the oldest request by itself; any collection order
+  assert driver.MAX_IN_FLIGHT == 3
+  h = [driver.submit(b) for b in batches[:4]]
   np.testing.assert_array_equal(h[0].result(), expect[0])
-  np.testing.assert_array_equal(h[2].result(), expect[2])
+  np.testing.assert_array_equal(h[3].result(), expect[3])
   np.testing.assert_array_equal(h[1].result(), expect[1])
+  np.testing.assert_array_equal(h[2].result(), expect[2])
   assert [r.shape for r in driver.serve_stream(batches)] == [(2, 100, 7)] * 5
   for g, e in zip(driver.serve_stream(iter(batches)), expect):
     np.testing.assert_array_equal(g, e)
