@@ -39,6 +39,8 @@ SIGNATURES = {
     'edet_pointwise_conv': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                     c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]),
+    'edet_class_argmax': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                  c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'edet_depthwise_conv': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'edet_conv2d': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -1,12 +1,7 @@
 // edet_pointwise_conv: argument checks + dispatch (tcgen05 path / SIMT cross-check kernel).
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace edet {
-namespace pwtc {
-int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bias,
-        const __half* residual, int ldr, __half* out, int ldo, int batch, int rows, int k, int nout,
-        int act, cudaStream_t stream);
-}
 
 // Plain CUDA-core GEMM used only to cross-check the tensor-core kernel on the device.
 // 64x64 output tile per 256-thread block, 4x4 outputs per thread, K in slabs of 16.
@@ -96,4 +91,22 @@ extern "C" int edet_pointwise_conv(const edet_half* a, int lda, const edet_half*
   }
   set_error("pointwise: unknown impl %d", impl);
   return EDET_ERR_INVALID;
+}
+
+extern "C" int edet_class_argmax(const edet_half* a, int lda, const edet_half* wt_padded,
+                                 const float* bias_padded, float* scores, int32_t* classes,
+                                 int anchor_begin, int total_anchors, int num_anchors, int batch,
+                                 int rows, int k, edet_stream_t stream) {
+  using namespace edet;
+  EDET_CHECK_ARG(a && wt_padded && bias_padded && scores && classes, "class_argmax: null pointer");
+  EDET_CHECK_ARG(batch > 0 && rows > 0 && k > 0 && k % 8 == 0 && lda % 8 == 0 && lda >= k,
+                 "class_argmax: bad shape (k=%d lda=%d)", k, lda);
+  EDET_CHECK_ARG(num_anchors > 0 && anchor_begin >= 0 &&
+                     anchor_begin + static_cast<long long>(rows) * num_anchors <= total_anchors,
+                 "class_argmax: anchors [%d, +%d*%d) exceed %d", anchor_begin, rows, num_anchors,
+                 total_anchors);
+  pwtc::ArgmaxArgs am{scores, classes, anchor_begin, total_anchors, num_anchors};
+  return pwtc::run(reinterpret_cast<const __half*>(a), lda, reinterpret_cast<const __half*>(wt_padded),
+                   1, bias_padded, nullptr, 0, nullptr, 0, batch, rows, k,
+                   num_anchors * 96, EDET_ACT_NONE, as_stream(stream), &am);
 }

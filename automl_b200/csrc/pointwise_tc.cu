@@ -19,6 +19,8 @@
 // Replaces Conv2D 1x1 (+BN, +swish, +skip) at the reference call sites listed in
 // include/automl_b200.h (edet_pointwise_conv).  Algorithmic HBM bytes per launch:
 //   2*(batch*rows*k + batch*rows*nout [+ same for residual]) + 2*wbatch*nout*k   (SURVEY 8d).
+#include <math_constants.h>
+
 #include "tc_common.cuh"
 
 namespace edet {
@@ -55,14 +57,34 @@ struct Params {
   int accum_stages;   // TMEM accumulator stages: 1..kMaxAccum, accum_stages * block_n <= 256 columns
   int wbatch, ldr, tmem_cols;
   int total_tiles;
+  int bias_floats;    // floats of the zero-padded bias staged in shared memory: whole N tiles
   const float* bias;
   const __half* residual;
   unsigned* sched;    // dynamic tile scheduler slot (tc_common.cuh)
+  // EPI_ARGMAX (class head -> pre-NMS): N tile n_blk = anchor n_blk, rows = pixels of one level
+  float* am_scores;       // [batch][am_total] sigmoid of the best class logit
+  int32_t* am_classes;    // [batch][am_total] its class index
+  int am_anchor_begin, am_total, am_num_anchors;
 };
+constexpr int EPI_STORE = 0, EPI_ARGMAX = 1;
+constexpr int kArgmaxCols = 96;   // columns per anchor in the padded class-head weights
 
 struct TileCoord {
   int b, m_blk, n_blk;
 };
+// Biases of 8 consecutive output columns from the copy of the (zero-padded) bias vector that the
+// prologue stages in shared memory: two ld.shared.v4 instead of two global loads plus the
+// ragged-edge branches in the middle of the MUFU / issue-bound epilogue.
+constexpr int kMaxBiasSmem = 8192;
+__device__ __forceinline__ void load_bias8(uint32_t smem_bias_u32, int col, float4& b0, float4& b1) {
+  const uint32_t a = smem_bias_u32 + static_cast<uint32_t>(col) * 4u;
+  // not volatile: the staged bias is constant for the kernel, so the loads may move freely
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(a));
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(a + 16u));
+}
+
 __device__ __forceinline__ TileCoord decode_tile(int t, const Params& p) {
   TileCoord c;
   c.n_blk = t % p.num_n_blocks;
@@ -72,7 +94,7 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const Params& p) {
   return c;
 }
 
-template <int ACT, bool HAS_RES, int TEAMS>
+template <int ACT, bool HAS_RES, int TEAMS, int EPI>
 __global__ void __launch_bounds__(Epi<TEAMS>::kThreads, 2)
 pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                     const __grid_constant__ CUtensorMap map_w,
@@ -87,7 +109,8 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
   constexpr int kEpiWarps = Epi<TEAMS>::kWarps;
   constexpr int kSlabBytes = Epi<TEAMS>::kSlabBytes;
   float* smem_bias = reinterpret_cast<float*>(smem_store + p.slabs_per_warp * kEpiWarps * kSlabBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + 2 * 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + p.bias_floats);
+  const uint32_t smem_bias_u32 = smem_u32(smem_bias);
   uint64_t* full_bar = bars;                       // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]
   uint64_t* tmem_full_bar = bars + 2 * kMaxStages;                 // [kMaxAccum]
@@ -122,6 +145,9 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_o)) : "memory");
   }
+  // bias (a constant, like the weights: read before the PDL wait) -> shared memory, zero padded
+  for (int i = threadIdx.x; i < p.bias_floats; i += blockDim.x)
+    smem_bias[i] = i < p.nout ? __ldg(p.bias + i) : 0.f;
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -293,17 +319,8 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
           for (int jj = 0; jj < 4; ++jj) {
             if (c_lo + jj * 8 < cols) {
               const int col = n0 + c * kStoreCols + c_lo + jj * 8;
-              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-              if (col < p.nout_pad8) {          // a whole group of 8 biases is in bounds
-                b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-              } else if (col < p.nout) {        // ragged last group (nout % 8 != 0)
-                float bb[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) bb[e] = (col + e < p.nout) ? __ldg(p.bias + col + e) : 0.f;
-                b0 = make_float4(bb[0], bb[1], bb[2], bb[3]);
-                b1 = make_float4(bb[4], bb[5], bb[6], bb[7]);
-              }
+              float4 b0, b1;
+              load_bias8(smem_bias_u32, col, b0, b1);
               float2 o2[4];
               o2[0] = __fadd2_rn(make_float2(v[jj * 8 + 0], v[jj * 8 + 1]), make_float2(b0.x, b0.y));
               o2[1] = __fadd2_rn(make_float2(v[jj * 8 + 2], v[jj * 8 + 3]), make_float2(b0.z, b0.w));
@@ -335,6 +352,71 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
         }
       }
     }
+    } else if constexpr (EPI == EPI_ARGMAX) {
+      // Class head fused with the class half of pre-NMS (tf2/postprocess.py:88-156 with
+      // max_nms_inputs == 0): an N tile is ONE anchor (90 class columns + 6 pad columns whose
+      // staged bias is -inf); the team (iter % TEAMS) owns the whole tile, lane = pixel.  Each
+      // logit is rounded to fp16 exactly as the storing epilogue would store it, then max / first
+      // arg-max / sigmoid as pre_nms_kernel does -> bit-identical scores and classes, without the
+      // [N, H, W, 810] logits ever reaching HBM.
+      const int e_warp = warp - 2;
+      const int quarter = warp & 3;
+      const int team = e_warp >> 2;
+      const int row_in_tile = quarter * 32 + lane;
+      for (int iter = 0;; ++iter) {
+        const int t = ring_get(iter, true);
+        if (t >= p.total_tiles) break;
+        const TileCoord tc = decode_tile(t, p);
+        const int as = iter % p.accum_stages;
+        const uint32_t aphase = static_cast<uint32_t>(iter / p.accum_stages) & 1u;
+        mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
+        tc_fence_after();
+        if (iter % TEAMS != team) {              // not this team's tile: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+          continue;
+        }
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(as * p.block_n);
+        const uint32_t bias_u32 = smem_bias_u32 + static_cast<uint32_t>(tc.n_blk * kArgmaxCols) * 4u;
+        float best = -CUDART_INF_F;
+        int best_c = 0;
+#pragma unroll
+        for (int g = 0; g < kArgmaxCols / 16; ++g) {
+          float v[16];
+          tc_ld16(taddr + g * 16, v);
+          tc_wait_ld();
+          if (g == kArgmaxCols / 16 - 1) {       // all TMEM reads of this warp are done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 b;
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                : "r"(bias_u32 + static_cast<uint32_t>(g * 16 + q * 4) * 4u));
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x = __half2float(__float2half_rn(__fadd_rn(v[q * 4 + e], bb[e])));
+              if (x > best) {                    // strict: the first maximum wins, like tf.argmax
+                best = x;
+                best_c = g * 16 + q * 4 + e;
+              }
+            }
+          }
+        }
+        const int row = tc.m_blk * BLOCK_M + row_in_tile;
+        if (row < p.rows) {
+          const size_t o = static_cast<size_t>(tc.b) * p.am_total + p.am_anchor_begin +
+                           static_cast<size_t>(row) * p.am_num_anchors + tc.n_blk;
+          p.am_scores[o] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-best)));
+          p.am_classes[o] = best_c;
+        }
+      }
     } else {
       // Units of 32 columns: warp (quarter, team) owns rows quarter*32..+31 of the tile and the
       // units u == team (mod TEAMS).  Each warp has private 2 KiB staging slabs ([32 rows] x 64
@@ -400,17 +482,8 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
               for (int jj = 0; jj < 2; ++jj) {
                 const int col = n0 + u * 32 + g * 16 + jj * 8;
-                float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                if (col < p.nout_pad8) {          // a whole group of 8 biases is in bounds
-                  b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                  b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                } else if (col < p.nout) {        // ragged last group (nout % 8 != 0)
-                  float bb[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) bb[e] = (col + e < p.nout) ? __ldg(p.bias + col + e) : 0.f;
-                  b0 = make_float4(bb[0], bb[1], bb[2], bb[3]);
-                  b1 = make_float4(bb[4], bb[5], bb[6], bb[7]);
-                }
+                float4 b0, b1;
+                load_bias8(smem_bias_u32, col, b0, b1);
                 float2 o2[4];
                 o2[0] = __fadd2_rn(make_float2(v[jj * 8 + 0], v[jj * 8 + 1]), make_float2(b0.x, b0.y));
                 o2[1] = __fadd2_rn(make_float2(v[jj * 8 + 2], v[jj * 8 + 3]), make_float2(b0.z, b0.w));
@@ -475,10 +548,10 @@ static int pick_block_n(int nout, int teams) {
   return teams == 3 ? 96 : 128;
 }
 
-template <int ACT, bool HAS_RES, int TEAMS>
+template <int ACT, bool HAS_RES, int TEAMS, int EPI = EPI_STORE>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo,
                   const Params& p, int grid, int smem_bytes, cudaStream_t stream) {
-  auto kern = pointwise_tc_kernel<ACT, HAS_RES, TEAMS>;
+  auto kern = pointwise_tc_kernel<ACT, HAS_RES, TEAMS, EPI>;
   static int configured[kMaxDevices];   // per instantiation and device; no API call once set
   if (int rc = ensure_dynamic_smem(kern, kSmemLimit, configured)) return rc;
   EDET_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(Epi<TEAMS>::kThreads), smem_bytes, stream, ma,
@@ -488,8 +561,17 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMa
 
 int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bias,
         const __half* residual, int ldr, __half* out, int ldo, int batch, int rows, int k, int nout,
-        int act, cudaStream_t stream) {
+        int act, cudaStream_t stream, const ArgmaxArgs* am) {
   Params p;
+  p.am_scores = nullptr; p.am_classes = nullptr;
+  p.am_anchor_begin = p.am_total = p.am_num_anchors = 0;
+  if (am) {
+    EDET_CHECK_ARG(nout == am->num_anchors * kArgmaxCols && !residual && act == EDET_ACT_NONE,
+                   "class_argmax: nout must be num_anchors * %d", kArgmaxCols);
+    p.am_scores = am->scores; p.am_classes = am->classes;
+    p.am_anchor_begin = am->anchor_begin; p.am_total = am->total_anchors;
+    p.am_num_anchors = am->num_anchors;
+  }
   p.batch = batch;
   p.rows = rows;
   p.k = k;
@@ -500,7 +582,7 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   // (measured on the D0 step: 4.68 ms with two teams, 4.53 ms with three, all layers);
   // edet_set_option("pw_teams", 2 | 3) forces a variant for A/B measurements.
   const int opt_teams = option_pw_teams();
-  const int teams = opt_teams ? opt_teams : 3;
+  const int teams = am ? 3 : (opt_teams ? opt_teams : 3);
   const int epi_warps = 4 * teams, slab_bytes = teams == 2 ? 4096 : 2048;
   p.block_n = pick_block_n(nout, teams);
   p.num_m_blocks = ceil_div(rows, BLOCK_M);
@@ -527,7 +609,11 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   // k-block / smem row pitch: 16 halves (32B swizzle) for K <= 16, 32 (64B) for K <= 32, else 64
   // (128B).  Two store slabs per epilogue warp when they fit; a wide N tile falls back first to
   // one slab, then to 32-wide k-blocks, so that the TMA ring stays >= 3 deep (>= 2 at worst).
-  const int ctrl = 2 * 256 * 4 + (2 * kMaxStages + 2 * kMaxAccum + 2 * kRing) * 8 + 16 + 4 * kRing;
+  // every column the epilogue can touch: whole N tiles (n_valid is rounded up to 16 inside a tile)
+  const int bias_cols = p.num_n_blocks * p.block_n;
+  EDET_CHECK_ARG(bias_cols <= kMaxBiasSmem, "pointwise_tc: nout %d too wide", nout);
+  p.bias_floats = bias_cols;
+  const int ctrl = p.bias_floats * 4 + (2 * kMaxStages + 2 * kMaxAccum + 2 * kRing) * 8 + 16 + 4 * kRing;
   int best_stages = 0, fixed = 0, stage_bytes = 0;
   auto plan = [&](int limit) {
     best_stages = 0;
@@ -577,9 +663,12 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
                      p.block_k)))
     return rc;
   // store box: [32 rows] x 64 columns (128B swizzle) for two teams, x 32 columns (64B) for three
-  if ((rc = make_map(&mo, out, nout, rows, batch, ldo, static_cast<uint64_t>(rows) * ldo, 32,
-                     teams == 2 ? 64 : 32)))
+  if (am) {
+    mo = mw;   // the arg-max epilogue stores nothing through TMA
+  } else if ((rc = make_map(&mo, out, nout, rows, batch, ldo, static_cast<uint64_t>(rows) * ldo, 32,
+                            teams == 2 ? 64 : 32))) {
     return rc;
+  }
 
   const int sm_count = device_sm_count();
   if (!sm_count) return EDET_ERR_CUDA;
@@ -587,6 +676,7 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   if (grid < sm_count) grid = sm_count;
   if (p.total_tiles < grid) grid = p.total_tiles;
   const bool has_res = residual != nullptr;
+  if (am) return launch<EDET_ACT_NONE, false, 3, EPI_ARGMAX>(ma, mw, mo, p, grid, smem_bytes, stream);
 
 #define EDET_PW_CASE(A)                                                                       \
   if (teams == 3)                                                                             \

@@ -38,30 +38,35 @@ pre_nms_kernel(const PreParams p, const float* __restrict__ anchors, float* __re
   const int n = blockIdx.y;
   const int pix0 = (blockIdx.x - lv.block_begin) * kPrePix;
   const int npix = min(kPrePix, lv.pixels - pix0);
-  // coalesced copy of npix * ld_cls halves (contiguous in NHWC)
-  const uint4* src = reinterpret_cast<const uint4*>(
-      lv.cls + (static_cast<size_t>(n) * lv.pixels + pix0) * p.ld_cls);
-  const int nvec = npix * p.ld_cls / 8;
-  for (int i = threadIdx.x; i < nvec; i += kPreThreads)
-    reinterpret_cast<uint4*>(cls_s)[i] = ldg_nc_v4(src + i);
-  __syncthreads();
+  const bool with_classes = lv.cls != nullptr;   // uniform; false: edet_class_argmax wrote them
+  if (with_classes) {
+    // coalesced copy of npix * ld_cls halves (contiguous in NHWC)
+    const uint4* src = reinterpret_cast<const uint4*>(
+        lv.cls + (static_cast<size_t>(n) * lv.pixels + pix0) * p.ld_cls);
+    const int nvec = npix * p.ld_cls / 8;
+    for (int i = threadIdx.x; i < nvec; i += kPreThreads)
+      reinterpret_cast<uint4*>(cls_s)[i] = ldg_nc_v4(src + i);
+    __syncthreads();
+  }
   const int t = threadIdx.x;
   if (t >= npix * p.num_anchors) return;
   const int pl = t / p.num_anchors, a = t - pl * p.num_anchors;
-  const __half* row = cls_s + pl * p.ld_cls + a * p.num_classes;
-  float best = __half2float(row[0]);
-  int best_c = 0;
-  for (int c = 1; c < p.num_classes; ++c) {
-    const float v = __half2float(row[c]);
-    if (v > best) {  // strict: first maximum wins, like tf.argmax
-      best = v;
-      best_c = c;
-    }
-  }
   const int anchor = lv.anchor_begin + (pix0 + pl) * p.num_anchors + a;
   const size_t o = static_cast<size_t>(n) * p.total_anchors + anchor;
-  scores[o] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-best)));
-  classes[o] = best_c;
+  if (with_classes) {
+    const __half* row = cls_s + pl * p.ld_cls + a * p.num_classes;
+    float best = __half2float(row[0]);
+    int best_c = 0;
+    for (int c = 1; c < p.num_classes; ++c) {
+      const float v = __half2float(row[c]);
+      if (v > best) {  // strict: first maximum wins, like tf.argmax
+        best = v;
+        best_c = c;
+      }
+    }
+    scores[o] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-best)));
+    classes[o] = best_c;
+  }
   // box decode (tf2/anchors.py:30-58), float32, no FMA contraction
   const uint2 bv = __ldg(reinterpret_cast<const uint2*>(
       lv.box + (static_cast<size_t>(n) * lv.pixels + pix0 + pl) * p.ld_box + a * 4));
@@ -714,7 +719,8 @@ extern "C" int edet_pre_nms(const edet_half* const* h_cls, const edet_half* cons
                             int num_anchors, int num_classes, const float* anchors, float* boxes,
                             float* scores, int32_t* classes, int n, edet_stream_t stream) {
   using namespace edet;
-  EDET_CHECK_ARG(h_cls && h_box && h_level_hw && anchors && boxes && scores && classes,
+  // h_cls == NULL: boxes only (scores / classes come from edet_class_argmax)
+  EDET_CHECK_ARG(h_box && h_level_hw && anchors && boxes && (!h_cls || (scores && classes)),
                  "pre_nms: null pointer");
   EDET_CHECK_ARG(levels >= 1 && levels <= kPreMaxLevels, "pre_nms: 1..8 levels");
   EDET_CHECK_ARG(ld_cls % 8 == 0 && ld_cls >= num_anchors * num_classes && ld_box % 4 == 0 &&
@@ -727,9 +733,9 @@ extern "C" int edet_pre_nms(const edet_half* const* h_cls, const edet_half* cons
   int blocks = 0, anchors_total = 0;
   for (int l = 0; l < levels; ++l) {
     PreLevel& lv = p.lv[l];
-    lv.cls = reinterpret_cast<const __half*>(h_cls[l]);
+    lv.cls = h_cls ? reinterpret_cast<const __half*>(h_cls[l]) : nullptr;
     lv.box = reinterpret_cast<const __half*>(h_box[l]);
-    EDET_CHECK_ARG(lv.cls && lv.box, "pre_nms: level %d pointer is null", l);
+    EDET_CHECK_ARG((lv.cls || !h_cls) && lv.box, "pre_nms: level %d pointer is null", l);
     lv.pixels = h_level_hw[2 * l] * h_level_hw[2 * l + 1];
     lv.block_begin = blocks;
     lv.anchor_begin = anchors_total;
@@ -737,7 +743,7 @@ extern "C" int edet_pre_nms(const edet_half* const* h_cls, const edet_half* cons
     anchors_total += lv.pixels * num_anchors;
   }
   p.total_anchors = anchors_total;
-  const size_t smem = static_cast<size_t>(kPrePix) * ld_cls * sizeof(__half);
+  const size_t smem = h_cls ? static_cast<size_t>(kPrePix) * ld_cls * sizeof(__half) : 0;
   EDET_CHECK_ARG(smem <= 96 * 1024, "pre_nms: ld_cls too large");
   if (smem > 48 * 1024)
     EDET_CHECK_CUDA(cudaFuncSetAttribute(pre_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -11,6 +11,16 @@ namespace pwtc {
 constexpr int BLOCK_M = 128;
 constexpr int UMMA_K = 16;
 
+// pointwise_tc.cu: the GEMM entry point shared by edet_pointwise_conv and edet_class_argmax
+struct ArgmaxArgs {
+  float* scores;         // [batch][total_anchors]
+  int32_t* classes;      // [batch][total_anchors]
+  int anchor_begin, total_anchors, num_anchors;
+};
+int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bias,
+        const __half* residual, int ldr, __half* out, int ldo, int batch, int rows, int k, int nout,
+        int act, cudaStream_t stream, const ArgmaxArgs* am = nullptr);
+
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

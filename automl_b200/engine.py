@@ -58,7 +58,8 @@ class Engine(object):
 
   def __init__(self, config, weights, batch_size, device='cuda:0', pw_impl=ops.PW_TCGEN05,
                use_cuda_graph=True, image_id_base=0, fuse_mbconv_front=False,
-               fuse_sepconv=True, fuse_sepconv_nodes=False, pipeline=True, defer_heads=False):
+               fuse_sepconv=True, fuse_sepconv_nodes=False, pipeline=True, defer_heads=False,
+               fuse_class_argmax=True):
     if not torch.cuda.is_available():
       raise RuntimeError('automl_b200.Engine needs a CUDA device; there is no CPU fallback')
     self.config = config
@@ -82,6 +83,14 @@ class Engine(object):
       defer_heads = os.environ['EDET_DEFER_HEADS'] != '0'
     self.defer_heads = bool(defer_heads and pipeline)   # see _run_pipelined
     self._deferred = None
+    # run(postprocess=True): the class-predict 1x1 conv computes max / arg-max / sigmoid over the
+    # classes in its epilogue (edet_class_argmax) and never writes the [N,H,W,810] logits;
+    # forward() always writes them.  Bit-identical detections either way.
+    if os.environ.get('EDET_FUSE_ARGMAX'):
+      fuse_class_argmax = os.environ['EDET_FUSE_ARGMAX'] != '0'
+    self.fuse_class_argmax = fuse_class_argmax
+    self._fused_target = None   # post-processing buffer set the fused class head writes to
+    self._logits_current = False   # the head output buffers hold the latest pass (forward())
     self.act = utils.activation_code(a.act_type)
     self._graph = None
     self._bb_split = None
@@ -394,6 +403,11 @@ class Engine(object):
     A, C = a.num_anchors, a.num_classes
     self.ld_cls, self.ld_box = _round_up(A * C, 8), _round_up(A * 4, 8)
     self.cls_out, self.box_out = {}, {}
+    nms_cfg = a.config.nms_configs
+    nms_cfg = nms_cfg.as_dict() if hasattr(nms_cfg, 'as_dict') else dict(nms_cfg)
+    self.fuse_class_argmax = bool(self.fuse_class_argmax and not int(nms_cfg.get('max_nms_inputs', 0) or 0)
+                                  and C <= ops.CLASS_ARGMAX_COLS and self.pw_impl == ops.PW_TCGEN05)
+    anchor_begin = 0
     for net, pred_c, ld in (('class', A * C, self.ld_cls), ('box', A * 4, self.ld_box)):
       scope = '%s_net' % net
       dws, pws, pbs = [], [], []
@@ -406,6 +420,17 @@ class Engine(object):
       pred_dw = self._dev(np.asarray(w[name + '/depthwise_kernel'], np.float64)[..., 0].reshape(9, F), f32)
       pred_wt = self._dev(np.asarray(w[name + '/pointwise_kernel'], np.float64)[0, 0].T, f16)  # [pred_c, F]
       pred_b = self._dev(w[name + '/bias'], f32)
+      pad_wt = pad_b = None
+      if net == 'class' and self.fuse_class_argmax:
+        # one anchor per 96-row block: rows a*96 + c; pad rows: zero weights, -inf bias
+        pcols = ops.CLASS_ARGMAX_COLS
+        kp = np.asarray(w[name + '/pointwise_kernel'], np.float64)[0, 0].T.reshape(A, C, F)
+        wpad = np.zeros((A, pcols, F), np.float64)
+        wpad[:, :C] = kp
+        bpad = np.full((A, pcols), -np.inf, np.float32)
+        bpad[:, :C] = np.asarray(w[name + '/bias'], np.float32).reshape(A, C)
+        pad_wt = self._dev(wpad.reshape(A * pcols, F), f16)
+        pad_b = self._dev(bpad.reshape(-1), f32)
       for level in a.levels:
         # every (tower, level) chain is independent: it becomes a parallel branch of the graph
         self._branch = '%s/l%d' % (scope, level)
@@ -436,8 +461,23 @@ class Engine(object):
         self._add('%s/l%d/dwp' % (scope, level),
                   lambda x=x, t=t, pred_dw=pred_dw: ops.depthwise_conv(x, t, pred_dw, None, utils.ACT_NONE, 3, 1),
                   kind='depthwise_k3s1', nbytes=4 * t.numel() + 18 * F, flops=18 * t.numel())
-        self._pw('%s/l%d/predict' % (scope, level), t, pred_wt, pred_b, out, utils.ACT_NONE,
-                 nout=pred_c)
+        if pad_wt is None:
+          self._pw('%s/l%d/predict' % (scope, level), t, pred_wt, pred_b, out, utils.ACT_NONE,
+                   nout=pred_c)
+        else:
+          def predict(t=t, out=out, begin=anchor_begin, pad_wt=pad_wt, pad_b=pad_b,
+                      pred_wt=pred_wt, pred_b=pred_b, impl=self.pw_impl, pred_c=pred_c):
+            ps = self._fused_target
+            if ps is not None:     # detect path: scores / classes straight into the post buffers
+              ops.class_argmax(t, pad_wt, pad_b, ps['scores'], ps['classes'], begin, A)
+            else:
+              ops.pointwise_conv(t, pred_wt, pred_b, out, utils.ACT_NONE, rows=t.numel() // F,
+                                 batch=1, nout=pred_c, impl=impl)
+          m = n * hh * ww
+          self._add('%s/l%d/predict' % (scope, level), predict, kind='pointwise_tc',
+                    nbytes=2 * m * F + 8 * m * A + 2 * pad_wt.numel(),
+                    flops=2 * m * F * pad_wt.shape[0])
+          anchor_begin += hh * ww * A
         (self.cls_out if net == 'class' else self.box_out)[level] = out
     self._branch = None
     self.num_network_ops = len(self._ops)
@@ -448,7 +488,6 @@ class Engine(object):
                                        list(p.aspect_ratios), p.anchor_scale, p.image_size)
     anc = self._dev(self.anchors.boxes, f32)
     self.total_anchors = K = self.anchors.boxes.shape[0]
-    nms_cfg = p.nms_configs.as_dict() if hasattr(p.nms_configs, 'as_dict') else dict(p.nms_configs)
     # max_nms_inputs > 0: NMS sees the top-k (anchor, class) pairs instead of one arg-max class
     # per anchor (tf2/postprocess.py:88-102)
     self.max_nms_inputs = topk = int(nms_cfg.get('max_nms_inputs', 0) or 0)
@@ -462,7 +501,7 @@ class Engine(object):
     cls_l = [self.cls_out[l] for l in a.levels]
     box_l = [self.box_out[l] for l in a.levels]
     level_hw = [a.level_hw[l] for l in a.levels]
-    self._pre_ops, self._nms_ops = [], []
+    self._pre_ops, self._nms_ops, self._pre_ops_full = [], [], []
     for sidx in range(2):
       ps = {
           'boxes': self._buf('boxes%d' % sidx, (n, K, 4), f32),
@@ -483,8 +522,14 @@ class Engine(object):
         self._pre_ops.append(lambda ps=ps: ops.pre_nms_topk(
             cls_l, box_l, level_hw, A, C, anc, ps['boxes'], ps['scores'], ps['classes'], ps['indices']))
       else:
-        self._pre_ops.append(lambda ps=ps: ops.pre_nms(cls_l, box_l, level_hw, A, C, anc,
-                                                       ps['boxes'], ps['scores'], ps['classes']))
+        full = lambda ps=ps: ops.pre_nms(cls_l, box_l, level_hw, A, C, anc,
+                                         ps['boxes'], ps['scores'], ps['classes'])
+        self._pre_ops_full.append(full)
+        if self.fuse_class_argmax:    # boxes only: the fused class head wrote scores / classes
+          self._pre_ops.append(lambda ps=ps: ops.pre_nms(None, box_l, level_hw, A, C, anc,
+                                                         ps['boxes'], None, None))
+        else:
+          self._pre_ops.append(full)
       self._nms_ops.append(lambda ps=ps: ops.nms_v5(
           ps['boxes'], ps['scores'], ps['classes'], ps['image_scales'], self.image_id_base,
           self.max_output_size, iou_t, score_t, tf_sigma, (float(H), float(W)),
@@ -608,6 +653,7 @@ class Engine(object):
     net_upto = self.num_network_ops
     if not postprocess:
       self.flush()
+      self._logits_current = True
       if self._head_pending:   # a pipelined step may still be reading / writing the head buffers
         torch.cuda.current_stream(self.device).wait_event(self._ev_pre[self._cur])
       if self.use_cuda_graph:
@@ -618,6 +664,7 @@ class Engine(object):
     sidx = self._step % 2
     ring = self._step % 4
     self._step += 1
+    self._logits_current = not self.fuse_class_argmax
     main = torch.cuda.current_stream(self.device)
     if self.pipeline:
       self._run_pipelined(sidx, main, after_nms, ring)
@@ -625,7 +672,11 @@ class Engine(object):
       if self._nms_pending[sidx]:
         main.wait_event(self._ev_nms[sidx])      # the NMS that last read this buffer set is done
       def net_and_pre():
-        self._run_ops(net_upto)
+        self._fused_target = self._post[sidx] if self.fuse_class_argmax else None
+        try:
+          self._run_ops(net_upto)
+        finally:
+          self._fused_target = None
         self._pre_ops[sidx]()
       if self.use_cuda_graph:
         self._graph_for(('net+pre', sidx), net_and_pre).replay()
@@ -680,8 +731,8 @@ class Engine(object):
       # sums of its first block onto a stale accumulator.
       if self._graph is None or 'bb1' not in self._graph:
         self._run_ops(net_upto)
-        self._pre_ops[0]()
-        self._pre_ops[1]()
+        for sx in (0, 1):
+          (self._pre_ops_full[sx] if self._pre_ops_full else self._pre_ops[sx])()
     self._replay('bb1', lambda: self._run_ops(split))
     if self.defer_heads:
       self._ev_early.record(main)
@@ -715,7 +766,11 @@ class Engine(object):
                    self._head_capture_stream)
       self._ev_head.record(hs)
       def heads_and_pre():
-        self._run_ops(net_upto, start=c0, priority=self._head_priority)
+        self._fused_target = self._post[sidx] if self.fuse_class_argmax else None
+        try:
+          self._run_ops(net_upto, start=c0, priority=self._head_priority)
+        finally:
+          self._fused_target = None
         self._pre_ops[sidx]()
       self._replay(('heads+pre', sidx), heads_and_pre, self._head_capture_stream)
       self._ev_pre[sidx].record(hs)
@@ -766,11 +821,17 @@ class Engine(object):
     return self.detections
 
   def pre_nms_only(self):
-    """Runs pre-NMS (class arg-max, sigmoid, box decode) on the current head outputs and returns
-    the buffer set {'boxes' [N,K,4], 'scores' [N,K], 'classes' [N,K]} (for the per-class NMS
-    path, automl_b200/postprocess.py)."""
+    """Pre-NMS (class arg-max, sigmoid, box decode) of the latest forward pass: the buffer set
+    {'boxes' [N,K,4], 'scores' [N,K], 'classes' [N,K]} (for the per-class NMS path,
+    automl_b200/postprocess.py).  After forward() it is computed here from the head outputs;
+    after run(postprocess=True) / detect() it is what that step already produced."""
     with torch.cuda.device(self.device):
-      self._pre_ops[self._cur]()
+      self.flush()
+      main = torch.cuda.current_stream(self.device)
+      if self._logits_current:
+        (self._pre_ops_full if self._pre_ops_full else self._pre_ops)[self._cur]()
+      elif self._head_pending or not self.pipeline:
+        main.wait_event(self._ev_pre[self._cur])
     return self._post[self._cur]
 
   def nms_fallback_count(self):
@@ -786,7 +847,17 @@ class Engine(object):
     """Times every launch of the list individually with CUDA events on the current stream
     (eager launches, not the graph) and returns op_info rows extended with 'ms' (mean)."""
     upto = len(self._ops) if postprocess else self.num_network_ops
+    self.flush()
+    if postprocess and self.fuse_class_argmax:
+      self._fused_target = self._post[0]       # time the launches run(postprocess=True) makes
+    try:
+      return self._profile_ops(iters, upto)
+    finally:
+      self._fused_target = None
+
+  def _profile_ops(self, iters, upto):
     with torch.cuda.device(self.device):
+      torch.cuda.synchronize()
       self._run_ops(upto, parallel_branches=False)  # warm-up
       torch.cuda.synchronize()
       acc = [0.0] * upto

@@ -28,6 +28,10 @@ def _ptr(t, dtype=None):
   return ctypes.c_void_p(t.data_ptr())
 
 
+def _round8(x):
+  return (x + 7) // 8 * 8
+
+
 def set_option(name, value):
   """Process-wide implementation switch (A/B measurements, tests): see edet_set_option."""
   _lib.call('edet_set_option', name.encode(), int(value))
@@ -170,13 +174,37 @@ def max_pool(x, out, pool, stride):
             pool[0], pool[1], stride[0], stride[1], _stream())
 
 
+CLASS_ARGMAX_COLS = 96   # columns per anchor of the padded class-head weights (edet_class_argmax)
+
+
+def class_argmax(a, wt_padded, bias_padded, scores, classes, anchor_begin, num_anchors):
+  """Class-predict 1x1 conv fused with the class half of pre-NMS for one level: a fp16
+  [N,H,W,F] (the depthwise output of the predict layer), wt_padded fp16 [num_anchors*96, F] (row
+  a*96 + c = class c of anchor a, zero rows for c >= num_classes), bias_padded fp32
+  [num_anchors*96] (-inf on the pad rows) -> scores fp32 / classes i32 [N, total_anchors] at
+  anchors anchor_begin + pixel*num_anchors + a."""
+  n, h, w, f = a.shape
+  assert wt_padded.shape == (num_anchors * CLASS_ARGMAX_COLS, f)
+  _lib.call('edet_class_argmax', _ptr(a, torch.float16), f, _ptr(wt_padded, torch.float16),
+            _ptr(bias_padded, torch.float32), _ptr(scores, torch.float32),
+            _ptr(classes, torch.int32), anchor_begin, scores.shape[1], num_anchors, n, h * w, f,
+            _stream())
+
+
 def pre_nms(cls_levels, box_levels, level_hw, num_anchors, num_classes, anchors, boxes, scores,
             classes):
-  """cls_levels[l] fp16 [N,H_l,W_l,ld_cls]; boxes fp32 [N,A,4], scores fp32 [N,A], classes i32."""
-  levels = len(cls_levels)
-  n = cls_levels[0].shape[0]
-  ld_cls, ld_box = cls_levels[0].shape[-1], box_levels[0].shape[-1]
-  cls_p = (ctypes.c_void_p * levels)(*[_ptr(t, torch.float16).value for t in cls_levels])
+  """cls_levels[l] fp16 [N,H_l,W_l,ld_cls]; boxes fp32 [N,A,4], scores fp32 [N,A], classes i32.
+  cls_levels=None: boxes only (scores / classes were written by class_argmax)."""
+  levels = len(box_levels)
+  n = box_levels[0].shape[0]
+  ld_box = box_levels[0].shape[-1]
+  if cls_levels is None:
+    ld_cls = _round8(num_anchors * num_classes)
+    cls_p = None
+    scores = classes = None
+  else:
+    ld_cls = cls_levels[0].shape[-1]
+    cls_p = (ctypes.c_void_p * levels)(*[_ptr(t, torch.float16).value for t in cls_levels])
   box_p = (ctypes.c_void_p * levels)(*[_ptr(t, torch.float16).value for t in box_levels])
   hw = (ctypes.c_int * (2 * levels))(*[v for pair in level_hw for v in pair])
   _lib.call('edet_pre_nms', cls_p, box_p, hw, levels, ld_cls, ld_box, num_anchors, num_classes,

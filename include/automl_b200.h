@@ -210,7 +210,28 @@ int edet_max_pool(const edet_half* in, edet_half* out, int n, int h, int wd, int
                   int pool_w, int stride_h, int stride_w, edet_stream_t stream);
 
 /*
+ * Class-predict 1x1 convolution of ONE pyramid level fused with the class half of pre-NMS: the
+ * [n, h, w, num_anchors * num_classes] logits are never written; per pixel and anchor the kernel
+ * rounds each logit to fp16 (what edet_pointwise_conv would have stored), takes max / first
+ * arg-max over the classes and the sigmoid of the max, exactly as edet_pre_nms does -- bit-identical
+ * scores and classes.  Replaces the pointwise half of class-predict (efficientdet_arch.py:166-174)
+ * + tf2/postprocess.py:88-156 (topk_class_boxes with max_nms_inputs == 0, sigmoid in pre_nms).
+ *   a            half [batch, rows, lda]: the predict layer's depthwise output (rows = h_l * w_l)
+ *   wt_padded    half [num_anchors * 96][k]: row a*96 + c = class c of anchor a (zero pad rows;
+ *                num_classes <= 96)
+ *   bias_padded  float32 [num_anchors * 96], -inf on the pad rows (they can never be the maximum)
+ *   scores float32 / classes int32 [batch, total_anchors], written at
+ *                anchor_begin + row * num_anchors + a
+ * Follow with edet_pre_nms(h_cls = NULL, ...) for the boxes.
+ */
+int edet_class_argmax(const edet_half* a, int lda, const edet_half* wt_padded,
+                      const float* bias_padded, float* scores, int32_t* classes, int anchor_begin,
+                      int total_anchors, int num_anchors, int batch, int rows, int k,
+                      edet_stream_t stream);
+
+/*
  * Pre-NMS: per image and anchor, max / argmax over classes, sigmoid, anchor box decode.
+ * h_cls == NULL: box decode only (scores / classes may be NULL; see edet_class_argmax).
  * Replaces tf2/postprocess.py:67-156 (merge_class_box_level_outputs, topk_class_boxes with
  * max_nms_inputs == 0, pre_nms) and tf2/anchors.py:30-58 (decode_box_outputs).
  *   h_cls[l] half [n, h_l, w_l, ld_cls] (anchor-major, class-minor: a*num_classes + c)

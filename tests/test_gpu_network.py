@@ -218,6 +218,11 @@ def test_detect_matches_oracle_postprocess_and_graph_replay():
   np.testing.assert_array_equal(det1[:, :, 0], np.asarray([[4.0] * 100, [5.0] * 100], np.float32))
 
   params = c.as_dict()
+  # detect() fuses the class head with the class arg-max (the logits are never stored): the
+  # network-only forward() of the same input writes them for the oracle's pre-NMS
+  assert eng.fuse_class_argmax
+  eng.forward(torch.from_numpy(x))
+  torch.cuda.synchronize()
   cls_l = [eng.cls_out[l][..., :810].float().cpu().numpy() for l in a.levels]
   box_l = [eng.box_out[l][..., :36].float().cpu().numpy() for l in a.levels]
   ref_boxes, ref_scores, ref_classes = po.pre_nms(params, cls_l, box_l)
@@ -285,7 +290,7 @@ def test_pipelined_steps_equal_sequential_steps(graph, defer):
   want, want_cls = [], []
   for x, sc in zip(xs, scales):
     want.append(seq.detect(x, sc).clone())
-    want_cls.append(seq.cls_out[a.levels[0]].clone())
+    want_cls.append(seq.box_out[a.levels[0]].clone())   # (the class logits are not stored by detect)
   torch.cuda.synchronize()
   assert not torch.equal(want[0][..., 1:5], want[1][..., 1:5])
   pipe = _engine(c, w, 2, use_cuda_graph=graph, pipeline=True, defer_heads=defer)
@@ -300,10 +305,42 @@ def test_pipelined_steps_equal_sequential_steps(graph, defer):
   torch.cuda.synchronize()
   for i in range(len(xs)):
     assert torch.equal(got[i], want[i]), 'step %d' % i
-  assert torch.equal(pipe.cls_out[a.levels[0]], want_cls[-1])
+  assert torch.equal(pipe.box_out[a.levels[0]], want_cls[-1])
   # a network-only forward after pipelined steps waits for the in-flight head stage
-  cls_out, _ = pipe.forward(xs[0])
+  _, box_out = pipe.forward(xs[0])
   torch.cuda.synchronize()
-  assert torch.equal(cls_out[a.levels[0]], want_cls[0][..., :cls_out[a.levels[0]].shape[-1]])
+  assert torch.equal(box_out[a.levels[0]], want_cls[0][..., :box_out[a.levels[0]].shape[-1]])
   # detect() right after (a held-back head stage is flushed by wait_detections)
   assert torch.equal(pipe.detect(xs[2], scales[2]), want[2])
+
+
+@pytest.mark.parametrize('name,size,n', [('efficientdet-d0', 128, 2), ('efficientdet-d0', (96, 160), 1),
+                                         ('efficientdet-d2', 128, 1)])
+def test_fused_class_argmax_equals_stored_logits(name, size, n):
+  """run(postprocess=True) computes max / arg-max / sigmoid over the classes in the epilogue of the
+  class-predict GEMM (edet_class_argmax; one anchor per 96-column tile) and never writes the
+  [N,H,W,810] logits.  Scores, classes, boxes and detections must be bit-identical to the engine
+  that stores the logits and runs the full pre-NMS kernel; the logit buffers stay untouched."""
+  c, a, w, x = _setup(name, size, n, seed=21)
+  xt = torch.from_numpy(x)
+  plain = _engine(c, w, n, fuse_class_argmax=False)
+  fused = _engine(c, w, n)
+  assert fused.fuse_class_argmax and not plain.fuse_class_argmax
+  for l in a.levels:
+    fused.cls_out[l].fill_(7.0)
+  d_plain = plain.detect(xt).clone()
+  d_fused = fused.detect(xt).clone()
+  torch.cuda.synchronize()
+  assert torch.equal(fused.scores, plain.scores)
+  assert torch.equal(fused.classes, plain.classes)
+  assert torch.equal(fused.boxes, plain.boxes)
+  assert torch.equal(d_fused, d_plain)
+  assert all(bool((fused.cls_out[l] == 7.0).all()) for l in a.levels)   # logits never written
+  # pre_nms_only(): after detect() the step's own tensors, after forward() recomputed from logits
+  ps = fused.pre_nms_only()
+  assert torch.equal(ps['scores'], plain.scores)
+  fused.forward(xt)
+  ps = fused.pre_nms_only()
+  torch.cuda.synchronize()
+  assert torch.equal(ps['scores'], plain.scores) and torch.equal(ps['classes'], plain.classes)
+  assert torch.equal(fused.cls_out[a.levels[0]], plain.cls_out[a.levels[0]])
