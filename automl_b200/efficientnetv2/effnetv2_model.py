@@ -377,6 +377,58 @@ class EffNetV2Model(object):
     return out
 
 
+  def serve_stream(self, batches):
+    """Pipelined __call__ over an iterable of host batches (float32 [N,H,W,3], ideally pinned):
+    the H2D copy of batch i+1 and the D2H copy of the feature map of batch i-1 overlap the network
+    of batch i (two copy streams for the two PCIe directions, device staging buffers on both
+    sides).  Yields the 'head_1x1' feature map of each batch, in order, as a pinned host float16
+    tensor that stays valid until two further results have been yielded."""
+    with torch.cuda.device(self.device):
+      if getattr(self, '_pipe', None) is None:
+        head = self.endpoints['head_1x1']
+        self._pipe = {
+            'in': [torch.empty_like(self.input) for _ in range(2)],
+            'out': [torch.empty_like(head) for _ in range(2)],
+            'host': [torch.empty(tuple(head.shape), dtype=head.dtype).pin_memory() for _ in range(2)],
+            'h2d': torch.cuda.Stream(device=self.device), 'd2h': torch.cuda.Stream(device=self.device),
+            'ev_h2d': [torch.cuda.Event() for _ in range(2)],
+            'ev_in_free': [torch.cuda.Event() for _ in range(2)],
+            'ev_out': [torch.cuda.Event() for _ in range(2)],
+            'ev_d2h': [torch.cuda.Event() for _ in range(2)],
+        }
+      p = self._pipe
+      main = torch.cuda.current_stream(self.device)
+      head = self.endpoints['head_1x1']
+      prev = None
+      for k, batch in enumerate(batches):
+        s = k % 2
+        t = torch.as_tensor(batch)
+        if tuple(t.shape) != tuple(self.input.shape):
+          raise ValueError('expected input shape %s, got %s' % (tuple(self.input.shape), tuple(t.shape)))
+        with torch.cuda.stream(p['h2d']):
+          p['h2d'].wait_event(p['ev_in_free'][s])        # batch k-2 has left this staging buffer
+          p['in'][s].copy_(t.to(torch.float32), non_blocking=True)
+          p['ev_h2d'][s].record(p['h2d'])
+        main.wait_event(p['ev_h2d'][s])
+        self.input.copy_(p['in'][s], non_blocking=True)
+        p['ev_in_free'][s].record(main)
+        self.run()
+        main.wait_event(p['ev_d2h'][s])                  # result k-2 has left this staging buffer
+        p['out'][s].copy_(head, non_blocking=True)
+        p['ev_out'][s].record(main)
+        with torch.cuda.stream(p['d2h']):
+          p['d2h'].wait_event(p['ev_out'][s])
+          p['host'][s].copy_(p['out'][s], non_blocking=True)
+          p['ev_d2h'][s].record(p['d2h'])
+        if prev is not None:
+          p['ev_d2h'][prev].synchronize()
+          yield p['host'][prev]
+        prev = s
+      if prev is not None:
+        p['ev_d2h'][prev].synchronize()
+        yield p['host'][prev]
+
+
 def get_model(model_name, model_config=None, include_top=False, weights=None, training=False,
               with_endpoints=False, **kwargs):
   """effnetv2_model.get_model (:661-722) for inference: returns the bound model instance

@@ -89,3 +89,24 @@ def test_backbone_parity_vs_oracle(name, size, batch, tol):
   again = model(torch.from_numpy(x)).clone()
   assert torch.equal(again, outs[0])                    # graph replay is deterministic
   print('%s worst rel-L2 %.2e' % (name, worst))
+
+
+@pytest.mark.gpu
+def test_serve_stream_equals_synchronous_calls():
+  """serve_stream keeps the H2D copy of batch i+1 and the D2H copy of result i-1 under the network
+  of batch i: five different batches must come back in order, equal to the synchronous calls."""
+  name = 'efficientnetv2-b0'
+  arch = effnetv2_model.EffNetV2Arch(name)
+  w = effnetv2_model.synthetic_weights(arch, 5)
+  model = effnetv2_model.get_model(name, weights=w, batch_size=2, image_size=64)
+  rng = np.random.default_rng(9)
+  batches = [torch.from_numpy(rng.uniform(-1, 1, size=(2, 64, 64, 3)).astype(np.float32)).pin_memory()
+             for _ in range(5)]
+  want = []
+  for b in batches:
+    want.append(model(b).cpu().clone())
+  got = [r.clone() for r in model.serve_stream(batches)]     # clone: the pinned buffers are reused
+  assert len(got) == 5
+  for g, e in zip(got, want):
+    assert torch.equal(g, e)
+  assert [tuple(r.shape) for r in model.serve_stream(iter(batches[:1]))] == [tuple(want[0].shape)]

@@ -326,6 +326,8 @@ def test_fused_class_argmax_equals_stored_logits(name, size, n):
   plain = _engine(c, w, n, fuse_class_argmax=False)
   fused = _engine(c, w, n)
   assert fused.fuse_class_argmax and not plain.fuse_class_argmax
+  fused.detect(xt)               # builds the graphs (the one eager warm-up forward writes logits)
+  torch.cuda.synchronize()
   for l in a.levels:
     fused.cls_out[l].fill_(7.0)
   d_plain = plain.detect(xt).clone()
