@@ -73,6 +73,8 @@ class Engine(object):
       fuse_mbconv_front = os.environ['EDET_FUSE_FRONT'] != '0'
     self.fuse_mbconv_front = fuse_mbconv_front
     self.fuse_sepconv = fuse_sepconv              # head tower layers: dw + pw in one kernel
+    if os.environ.get('EDET_FUSE_NODES'):
+      fuse_sepconv_nodes = os.environ['EDET_FUSE_NODES'] != '0'
     self.fuse_sepconv_nodes = fuse_sepconv_nodes  # BiFPN nodes (measured slower than the pair)
     # pipeline: run(postprocess=True) overlaps the backbone of step i+1 (main stream) with the
     # feature network + heads + pre-NMS of step i (head stream) and the NMS of step i (NMS stream)
