@@ -1,22 +1,22 @@
-// Separable convolution of the feature network and the head towers as ONE kernel:
-//   [resample + weighted fusion (+ act)]  ->  depthwise 3x3 'SAME'  ->  pointwise 1x1 on the tensor
-//   cores (+ bias, BN folded) (+ act)
+// Separable convolution of a head tower layer as ONE kernel:
+//   depthwise 3x3 'SAME'  ->  pointwise 1x1 on the tensor cores (+ bias, BN folded) (+ act)
 // The depthwise result never reaches HBM: it is written as fp16 straight into the 128B-swizzled
 // K-major shared-memory tile that tcgen05.mma reads as its A operand.
 //
-// Replaces, per BiFPN node   efficientdet_arch.py:478-544 (resample_feature_map of every input,
-//                            fuse_features :55-132, activation, SeparableConv2D + BN)
-//          per tower layer   efficientdet_arch.py:149-191 / 206-249 (SeparableConv2D, per-level
-//                            BN, activation)
-// Algorithmic HBM bytes per launch: 2*N*c*(sum_inputs h_i*w_i) + 2*N*h*w*nout + weights -- the
-// [N,h,w,c] depthwise output (written and read back by the fuse_dw + pointwise pair) is gone.
+// Replaces, per tower layer, efficientdet_arch.py:149-191 / 206-249 (SeparableConv2D, per-level
+// BN, activation).  Algorithmic HBM bytes per launch: 2*N*h*w*(c + nout) + weights -- the
+// [N,h,w,c] depthwise output (written and read back by a depthwise + pointwise pair) is gone.
 //
 // One CTA = one 8x16 output tile (128 pixels = the M of one UMMA), persistent over tiles:
-//   1. all warps: fused (+activated) input tile with its 1-pixel halo -> fp32 smem, 64 channels
-//      at a time
-//   2. all warps: depthwise 3x3 from smem -> fp16 A tile [128 px][c] (swizzled K-major atoms)
-//   3. one thread: tcgen05.mma  D[128 px][nout] = A * W^T  (W loaded once per CTA by TMA)
-//   4. all warps: TMEM -> +bias, act -> fp16 -> global (32 contiguous bytes per tcgen05.ld)
+//   1. all warps: depthwise 3x3 -> fp16 A tile [128 px][c] (swizzled K-major atoms)
+//   2. one thread: tcgen05.mma  D[128 px][nout] = A * W^T  (W loaded once per CTA by TMA)
+//   3. all warps: TMEM -> +bias, act -> fp16 -> global (32 contiguous bytes per tcgen05.ld)
+//
+// The whole-BiFPN-node form of this kernel (resample + weighted fusion + activation in front of
+// the depthwise) was removed in round 2: measured on the D0 step it was slower than the
+// fuse_dw + pointwise pair in both rounds (4.21 vs 3.76 ms per step with the pipelined engine):
+// fusion, depthwise, MMA and epilogue serialise inside a CTA whose 100 KB of staging leaves two
+// CTAs per SM.
 #include "fuse_common.cuh"
 #include "tc_common.cuh"
 
@@ -25,11 +25,8 @@ namespace sepc {
 
 using namespace pwtc;
 
-constexpr int kThreads = 256;
 constexpr int TH = 8, TW = 16;            // output tile: 128 pixels
 constexpr int HT = TH + 2, WT = TW + 2;   // with halo
-constexpr int CB = 64;                    // channels per fused block = one 128-byte swizzle atom
-constexpr int G = CB / 8;
 constexpr int kMaxC = 128, kMaxN = 128;
 constexpr int kAtomBytesA = 128 * 128;    // [128 rows][64 halves]
 
@@ -43,204 +40,6 @@ struct Params {
   int tiles_x, tiles_y, total_tiles;
   unsigned* sched;        // dynamic tile scheduler slot (direct kernel)
 };
-
-template <int ACT_PRE, int ACT_POST>
-__global__ void __launch_bounds__(kThreads, 3)
-sepconv_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
-  pdl_launch_dependents();
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* smem_a = smem;                                   // katoms x [128][64] halves
-  uint8_t* smem_b = smem_a + p.katoms * kAtomBytesA;        // katoms x [npad][64] halves
-  float* fused = reinterpret_cast<float*>(smem_b + p.katoms * p.b_atom_bytes);   // [HT*WT][CB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(fused + HT * WT * CB);
-  const uint32_t w_bar = smem_u32(bars);       // weights landed
-  const uint32_t mma_bar = smem_u32(bars + 1);  // accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    mbar_init(w_bar, 1);
-    mbar_init(mma_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
-  }
-  if (warp == 0) {
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"(static_cast<uint32_t>(p.tmem_cols))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) {   // the weights are constants: no need to wait for the producer kernel
-    mbar_expect_tx(w_bar, static_cast<uint32_t>(p.katoms * p.npad * 128));
-    for (int kb = 0; kb < p.katoms; ++kb)
-      tma_load_3d(smem_u32(smem_b + kb * p.b_atom_bytes), &map_w, w_bar, kb * 64, 0, 0);
-  }
-  pdl_wait_prior();
-
-  const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(p.npad >> 3) << 17) |
-                         (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
-  const uint32_t a_u32 = smem_u32(smem_a);
-  uint32_t mma_phase = 0;
-  bool weights_ready = false;   // thread 0 only
-  const int c = p.c;
-
-  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-    const int tx_i = t % p.tiles_x;
-    const int ty_i = (t / p.tiles_x) % p.tiles_y;
-    const int n = t / (p.tiles_x * p.tiles_y);
-    const int y0 = ty_i * TH, x0 = tx_i * TW;
-
-    for (int cb = 0; cb < p.katoms; ++cb) {
-      const int c0 = cb * CB;
-      const int groups = min(G, (c - c0) >> 3);
-      // ---- 1. fused + activated map of the tile and its halo, channels [c0, c0 + 64) ---------
-      for (int item = threadIdx.x; item < HT * WT * G; item += kThreads) {
-        const int g = item % G, pix = item / G;
-        const int ty = pix / WT, tx = pix % WT;
-        const int y = y0 + ty - 1, x = x0 + tx - 1;
-        float acc[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        if (g < groups && y >= 0 && y < p.h && x >= 0 && x < p.w) {
-          const int ch = c0 + g * 8;
-          for (int i = 0; i < p.fuse.n_inputs; ++i) {
-            const FuseIn& fi = p.fuse.in[i];
-            const __half* base = fi.ptr + static_cast<size_t>(n) * fi.h * fi.w * c;
-            float v[8];
-            resample8(fi, base, c, y, x, ch, v);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], fi.weight, acc[e]);
-          }
-          if (ACT_PRE != EDET_ACT_NONE) {
-#pragma unroll
-            for (int e = 0; e < 8; e += 4) {
-              float2 a = make_float2(acc[e], acc[e + 1]), b = make_float2(acc[e + 2], acc[e + 3]);
-              apply_act4<ACT_PRE>(a, b);
-              acc[e] = a.x; acc[e + 1] = a.y; acc[e + 2] = b.x; acc[e + 3] = b.y;
-            }
-          }
-        }
-        float4* dst = reinterpret_cast<float4*>(fused + pix * CB + g * 8);
-        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-      }
-      __syncthreads();
-      // ---- 2. depthwise 3x3 -> fp16 A atom cb (16-byte piece j of row r at (j ^ (r & 7))) ------
-      for (int item = threadIdx.x; item < TH * TW * G; item += kThreads) {
-        const int g = item % G, row = item / G;
-        const int ty = row / TW, tx = row % TW;
-        float acc[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        if (g < groups && y0 + ty < p.h && x0 + tx < p.w) {
-          const int ch = c0 + g * 8;
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const float4* wp4 = reinterpret_cast<const float4*>(
-                  p.dw_w + static_cast<size_t>(ky * 3 + kx) * c + ch);
-              const float4 w0 = __ldg(wp4), w1 = __ldg(wp4 + 1);
-              const float wf[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-              const float4* src =
-                  reinterpret_cast<const float4*>(fused + ((ty + ky) * WT + tx + kx) * CB + g * 8);
-              const float4 a = src[0], b = src[1];
-              acc[0] = fmaf(a.x, wf[0], acc[0]); acc[1] = fmaf(a.y, wf[1], acc[1]);
-              acc[2] = fmaf(a.z, wf[2], acc[2]); acc[3] = fmaf(a.w, wf[3], acc[3]);
-              acc[4] = fmaf(b.x, wf[4], acc[4]); acc[5] = fmaf(b.y, wf[5], acc[5]);
-              acc[6] = fmaf(b.z, wf[6], acc[6]); acc[7] = fmaf(b.w, wf[7], acc[7]);
-            }
-          }
-        }
-        const uint4 packed = float_to_half8(acc);   // zeros for padding channels / pixels
-        const uint32_t dst = a_u32 + cb * kAtomBytesA + row * 128 + ((g ^ (row & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed.x),
-                     "r"(packed.y), "r"(packed.z), "r"(packed.w)
-                     : "memory");
-      }
-      if (cb + 1 < p.katoms) __syncthreads();   // `fused` is rewritten by the next channel block
-    }
-    fence_proxy_async_smem();   // generic-proxy writes of A -> visible to the tensor core
-    tc_fence_before();
-    __syncthreads();
-    // ---- 3. D = A * W^T ----------------------------------------------------------------------
-    if (threadIdx.x == 0) {
-      if (!weights_ready) {
-        mbar_wait(w_bar, 0);
-        weights_ready = true;
-      }
-      tc_fence_after();
-      for (int kb = 0; kb < p.katoms; ++kb) {
-        const uint64_t da = make_smem_desc(a_u32 + kb * kAtomBytesA, 1024, 2);
-        const uint64_t db = make_smem_desc(smem_u32(smem_b + kb * p.b_atom_bytes), 1024, 2);
-        const int ksteps = min(4, (p.kpad - kb * 64) >> 4);
-        for (int ks = 0; ks < ksteps; ++ks)
-          tc_mma_f16(tmem_base, da + static_cast<uint64_t>(ks * 2), db + static_cast<uint64_t>(ks * 2),
-                     idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-      }
-      tc_commit(mma_bar);
-    }
-    mbar_wait(mma_bar, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after();
-    // ---- 4. epilogue: warp w reads TMEM lanes 32*(w&3).., column half (w>>2) -------------------
-    {
-      const int quarter = warp & 3, half_id = warp >> 2;
-      const int row = quarter * 32 + lane;
-      const int y = y0 + row / TW, x = x0 + row % TW;
-      const bool ok = y < p.h && x < p.w;
-      __half* orow = p.out + ((static_cast<size_t>(n) * p.h + y) * p.w + x) * p.ldo;
-      const int nchunks = p.npad >> 4, split = (nchunks + 1) >> 1;
-      const int cbeg = half_id == 0 ? 0 : split, cend = half_id == 0 ? split : nchunks;
-      for (int ci = cbeg; ci < cend; ++ci) {
-        const int col = ci * 16;
-        float v[16];
-        tc_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(col), v);
-        tc_wait_ld();
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int cc = col + hh * 8;
-          if (ok && cc < p.nout) {   // nout % 8 == 0
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cc));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cc + 4));
-            float2 r0 = __fadd2_rn(make_float2(v[hh * 8 + 0], v[hh * 8 + 1]), make_float2(b0.x, b0.y));
-            float2 r1 = __fadd2_rn(make_float2(v[hh * 8 + 2], v[hh * 8 + 3]), make_float2(b0.z, b0.w));
-            float2 r2 = __fadd2_rn(make_float2(v[hh * 8 + 4], v[hh * 8 + 5]), make_float2(b1.x, b1.y));
-            float2 r3 = __fadd2_rn(make_float2(v[hh * 8 + 6], v[hh * 8 + 7]), make_float2(b1.z, b1.w));
-            if (ACT_POST != EDET_ACT_NONE) {
-              apply_act4<ACT_POST>(r0, r1);
-              apply_act4<ACT_POST>(r2, r3);
-            }
-            const float o[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};
-            *reinterpret_cast<uint4*>(orow + cc) = float_to_half8(o);
-          }
-        }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();   // TMEM, A and `fused` are free for the next tile
-    tc_fence_after();
-  }
-
-  if (threadIdx.x == 0 && !weights_ready) mbar_wait(w_bar, 0);   // never exit with a TMA in flight
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 0) {
-    __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(static_cast<uint32_t>(p.tmem_cols))
-                 : "memory");
-  }
-}
 
 // ---- single-input form (head tower layers): depthwise straight from global memory ------------
 // No fusion and no pre-activation, so the input tile needs no staging: each thread owns one
@@ -706,16 +505,6 @@ static int launch_direct(const CUtensorMap& mw, const Params& p, int grid, int s
   return EDET_OK;
 }
 
-template <int PRE, int POST>
-static int launch(const CUtensorMap& mw, const Params& p, int grid, int smem_bytes,
-                  cudaStream_t stream) {
-  auto kern = sepconv_kernel<PRE, POST>;
-  static int configured[kMaxDevices];
-  if (int rc = ensure_dynamic_smem(kern, 232448, configured)) return rc;
-  EDET_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem_bytes, stream, mw, p));
-  return EDET_OK;
-}
-
 }  // namespace sepc
 }  // namespace edet
 
@@ -756,11 +545,10 @@ extern "C" int edet_sepconv(const edet_fuse_input* h_inputs, int n_inputs, int p
   if (!p.sched) return EDET_ERR_CUDA;
   const bool direct = n_inputs == 1 && p.fuse.in[0].mode == EDET_RS_SAME &&
                       p.fuse.in[0].weight == 1.0f && pre_act == EDET_ACT_NONE;
-  int smem_bytes = 1024 + p.katoms * (kAtomBytesA + p.b_atom_bytes) + 64;
-  if (!direct) smem_bytes += HT * WT * CB * 4;
+  const int smem_bytes = 1024 + p.katoms * (kAtomBytesA + p.b_atom_bytes) + 64;
   int per_sm = 232448 / (smem_bytes + 1024);
   if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;
-  const int cap = direct ? 4 : 3;
+  const int cap = 4;
   if (per_sm > cap) per_sm = cap;
   if (per_sm < 1) per_sm = 1;
   const int grid = p.total_tiles < per_sm * sm_count ? p.total_tiles : per_sm * sm_count;
@@ -786,14 +574,7 @@ extern "C" int edet_sepconv(const edet_fuse_input* h_inputs, int n_inputs, int p
     set_error("sepconv: unsupported activation %d", post_act);
     return EDET_ERR_UNSUPPORTED;
   }
-#define EDET_SEPC(PRE, POST) \
-  if (pre_act == PRE && post_act == POST) return launch<PRE, POST>(mw, p, grid, smem_bytes, s)
-  EDET_SEPC(EDET_ACT_SWISH, EDET_ACT_NONE);
-  EDET_SEPC(EDET_ACT_NONE, EDET_ACT_SWISH);
-  EDET_SEPC(EDET_ACT_RELU6, EDET_ACT_NONE);
-  EDET_SEPC(EDET_ACT_NONE, EDET_ACT_RELU6);
-  EDET_SEPC(EDET_ACT_NONE, EDET_ACT_NONE);
-#undef EDET_SEPC
-  set_error("sepconv: unsupported activation pair (%d, %d)", pre_act, post_act);
+  set_error("sepconv: only the single-input form (one RS_SAME input, weight 1, no pre-activation) "
+            "exists; BiFPN nodes run edet_fuse_dw + edet_pointwise_conv");
   return EDET_ERR_UNSUPPORTED;
 }

@@ -58,7 +58,7 @@ class Engine(object):
 
   def __init__(self, config, weights, batch_size, device='cuda:0', pw_impl=ops.PW_TCGEN05,
                use_cuda_graph=True, image_id_base=0, fuse_mbconv_front=False,
-               fuse_sepconv=True, fuse_sepconv_nodes=False, pipeline=True, defer_heads=False,
+               fuse_sepconv=True, pipeline=True, defer_heads=False,
                fuse_class_argmax=True):
     if not torch.cuda.is_available():
       raise RuntimeError('automl_b200.Engine needs a CUDA device; there is no CPU fallback')
@@ -73,9 +73,6 @@ class Engine(object):
       fuse_mbconv_front = os.environ['EDET_FUSE_FRONT'] != '0'
     self.fuse_mbconv_front = fuse_mbconv_front
     self.fuse_sepconv = fuse_sepconv              # head tower layers: dw + pw in one kernel
-    if os.environ.get('EDET_FUSE_NODES'):
-      fuse_sepconv_nodes = os.environ['EDET_FUSE_NODES'] != '0'
-    self.fuse_sepconv_nodes = fuse_sepconv_nodes  # BiFPN nodes (measured slower than the pair)
     # pipeline: run(postprocess=True) overlaps the backbone of step i+1 (main stream) with the
     # feature network + heads + pre-NMS of step i (head stream) and the NMS of step i (NMS stream)
     if os.environ.get('EDET_PIPELINE'):        # A/B switch for scripts / bench runs
@@ -341,7 +338,7 @@ class Engine(object):
     mode_code = {'same': ops.RS_SAME, 'up': ops.RS_UP, 'down': ops.RS_DOWN}
     # the fused separable-conv kernel covers D0-D2 widths and the swish / relu6 networks; wider
     # feature networks keep the fuse_dw + pointwise pair
-    fuse_sep = ((self.fuse_sepconv or self.fuse_sepconv_nodes) and F <= ops.SEPCONV_MAX_C and
+    fuse_sep = (self.fuse_sepconv and F <= ops.SEPCONV_MAX_C and
                 act in (utils.ACT_SWISH, utils.ACT_RELU6))
     for ci, cell in enumerate(a.cells):
       cell_feats = list(pyramid)
@@ -382,19 +379,12 @@ class Engine(object):
         hh, ww = node.hw
         out = self._buf(node.scope + '/out', (n, hh, ww, F))
         in_bytes = 2 * sum(sp[0].numel() for sp in specs)
-        if fuse_sep and self.fuse_sepconv_nodes:
-          self._add(node.scope + '/sepconv',
-                    lambda specs=specs, dw_w=dw_w, pw_wt=pw_wt, pw_b=pw_b, out=out:
-                    ops.sepconv(specs, act, dw_w, pw_wt, pw_b, out, utils.ACT_NONE),
-                    kind='sepconv_tc', nbytes=in_bytes + 2 * out.numel() + 18 * F + 2 * F * F,
-                    flops=2 * (9 + F) * out.numel(), needs=needs)
-        else:
-          tmp = self._buf(node.scope + '/fused_dw', (n, hh, ww, F))
-          self._add(node.scope + '/fuse_dw',
-                    lambda specs=specs, dw_w=dw_w, tmp=tmp: ops.fuse_dw(specs, dw_w, tmp, act),
-                    kind='bifpn_fuse_dw', nbytes=in_bytes + 2 * tmp.numel() + 18 * F,
-                    flops=2 * 9 * tmp.numel(), needs=needs)
-          self._pw(node.scope + '/pw', tmp, pw_wt, pw_b, out, utils.ACT_NONE)
+        tmp = self._buf(node.scope + '/fused_dw', (n, hh, ww, F))
+        self._add(node.scope + '/fuse_dw',
+                  lambda specs=specs, dw_w=dw_w, tmp=tmp: ops.fuse_dw(specs, dw_w, tmp, act),
+                  kind='bifpn_fuse_dw', nbytes=in_bytes + 2 * tmp.numel() + 18 * F,
+                  flops=2 * 9 * tmp.numel(), needs=needs)
+        self._pw(node.scope + '/pw', tmp, pw_wt, pw_b, out, utils.ACT_NONE)
         cell_feats.append(out)
       pyramid = [cell_feats[cell['out_index'][l]] for l in a.levels]
       if ci == 0:

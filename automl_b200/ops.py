@@ -155,8 +155,9 @@ SEPCONV_MAX_C = 128   # edet_sepconv limits (c and nout)
 
 
 def sepconv(specs, pre_act, dw_w, pw_wt, bias, out, post_act, nout=None):
-  """Fused fuse_dw + pointwise_conv: specs as in fuse_dw, pw_wt fp16 [nout, c], out fp16
-  [N,h,w,ldo] (ldo >= nout)."""
+  """Head tower layer in one kernel (depthwise 3x3 + pointwise 1x1): specs = ONE (tensor,
+  RS_SAME, None, 1.0) input, pre_act ACT_NONE; pw_wt fp16 [nout, c], out fp16 [N,h,w,ldo]
+  (ldo >= nout)."""
   n, h, wd, ldo = out.shape
   c = pw_wt.shape[-1]
   n_out = nout if nout is not None else pw_wt.shape[0]

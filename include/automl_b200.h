@@ -190,14 +190,15 @@ typedef struct {
 int edet_fuse_dw(const edet_fuse_input* h_inputs, int n_inputs, const float* dw_w,
                  edet_half* out, int n, int h, int wd, int c, int act, edet_stream_t stream);
 
-/* Fused separable convolution of the feature network / head towers (tcgen05):
- *   out = post_act( pointwise( depthwise3x3( pre_act( sum_i weight_i * resample_i(input_i) ) ) ) + bias )
- * i.e. edet_fuse_dw followed by edet_pointwise_conv without the [n,h,w,c] intermediate in HBM
+/* Fused separable convolution of a head tower layer (tcgen05):
+ *   out = post_act( pointwise( depthwise3x3( input ) ) + bias )
+ * i.e. a depthwise conv followed by edet_pointwise_conv without the [n,h,w,c] intermediate in HBM
  * (the depthwise result is rounded to fp16 in shared memory, exactly as the pair rounds it in
- * global memory).  Replaces a whole BiFPN node (efficientdet_arch.py:478-544: pre_act = the
- * network activation, post_act = NONE) or a head tower layer (:149-191 / :206-249: one input,
- * weight 1, pre_act = NONE, post_act = the activation after the per-level BN folded into
- * pw_wt / bias).
+ * global memory).  Replaces a head tower layer (efficientdet_arch.py:149-191 / :206-249: the
+ * activation comes after the per-level BN folded into pw_wt / bias).  h_inputs: ONE input with
+ * mode EDET_RS_SAME and weight 1, pre_act = EDET_ACT_NONE; anything else returns
+ * EDET_ERR_UNSUPPORTED (the whole-BiFPN-node form was removed in round 2: slower than
+ * edet_fuse_dw + edet_pointwise_conv).
  *   dw_w float32 [9][c], pw_wt half [nout][c], bias float32 [nout], out half [n,h,wd,ldo]
  *   c % 8 == 0, c <= 128; nout % 8 == 0, nout <= 128; ldo >= nout, ldo % 8 == 0. */
 int edet_sepconv(const edet_fuse_input* h_inputs, int n_inputs, int pre_act, const float* dw_w,

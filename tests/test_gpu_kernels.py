@@ -427,12 +427,10 @@ def test_conv2d_tc(case):
 
 SEP_CASES = [
     # n, (h, w), c, nout, pre, post, inputs [(mode, (h, w))]
-    (2, (20, 20), 64, 64, utils.ACT_SWISH, utils.ACT_NONE, ['same', 'up']),        # td node
-    (2, (10, 10), 64, 64, utils.ACT_SWISH, utils.ACT_NONE, ['same', 'same', 'down']),  # bu node
-    (1, (13, 21), 88, 88, utils.ACT_SWISH, utils.ACT_NONE, ['same', 'up']),        # D1 width, 2 atoms
+    (1, (13, 21), 88, 88, utils.ACT_NONE, utils.ACT_SWISH, ['same']),              # D1 width, 2 atoms
     (2, (5, 5), 64, 64, utils.ACT_NONE, utils.ACT_SWISH, ['same']),                # tower layer, tiny level
     (1, (40, 40), 64, 64, utils.ACT_NONE, utils.ACT_SWISH, ['same']),              # several tiles per CTA
-    (1, (9, 17), 112, 112, utils.ACT_RELU6, utils.ACT_NONE, ['same', 'down']),
+    (1, (9, 17), 112, 112, utils.ACT_NONE, utils.ACT_RELU6, ['same']),             # D2 width
     (3, (80, 80), 64, 64, utils.ACT_NONE, utils.ACT_SWISH, ['same']),              # persistent loop
     (2, (33, 47), 64, 64, utils.ACT_NONE, utils.ACT_SWISH, ['same']),              # ragged tiles (TMA zero fill)
     (1, (17, 9), 48, 48, utils.ACT_NONE, utils.ACT_RELU6, ['same']),               # c < 64: box wider than the tensor
@@ -443,13 +441,12 @@ SEP_CASES = [
 @pytest.mark.parametrize('impl', [0, 1])
 @pytest.mark.parametrize('case', SEP_CASES)
 def test_sepconv(case, impl):
-  """edet_sepconv == edet_fuse_dw + edet_pointwise_conv bit for bit (same fp16 rounding of the
-  depthwise result), and both match the float64 restatement.  impl 0 / 1: input tile of the
-  single-input form staged by TMA / loaded straight from global memory."""
+  """edet_sepconv (a head tower layer: depthwise 3x3 + pointwise in one kernel) == edet_fuse_dw +
+  edet_pointwise_conv bit for bit (same fp16 rounding of the depthwise result), and both match
+  the float64 restatement.  impl 0 / 1: input tile staged by TMA / loaded straight from global
+  memory."""
   ops = _ops()
   n, (h, w), c, nout, pre, post, modes = case
-  if impl == 1 and len(modes) > 1:
-    pytest.skip('the option only affects the single-input form')
   ops.set_option('sepconv_impl', impl)
   g = torch.Generator().manual_seed(31 + h + c)
   specs, ref_in = [], []
@@ -764,3 +761,17 @@ def test_per_class_nms_bad_method():
                       None, None, 90, 100, 'median', None, torch.empty(1, 100, 7, device=DEV),
                       torch.empty(1, 100, dtype=torch.int32, device=DEV),
                       torch.empty(1, dtype=torch.int32, device=DEV))
+
+
+def test_sepconv_rejects_the_removed_node_form():
+  """The whole-BiFPN-node form (several inputs / pre-activation) was removed: loud error, no fallback."""
+  ops = _ops()
+  from automl_b200 import _lib
+  a = torch.zeros(1, 8, 8, 64, dtype=torch.float16, device=DEV)
+  out = torch.empty(1, 8, 8, 64, dtype=torch.float16, device=DEV)
+  dw = torch.zeros(9, 64, device=DEV)
+  pw = torch.zeros(64, 64, dtype=torch.float16, device=DEV)
+  b = torch.zeros(64, device=DEV)
+  with pytest.raises(_lib.EdetError):
+    ops.sepconv([(a, ops.RS_SAME, None, 0.5), (a, ops.RS_SAME, None, 0.5)], utils.ACT_SWISH, dw, pw, b,
+                out, utils.ACT_NONE)
