@@ -284,8 +284,11 @@ sepconv_direct_kernel(const __grid_constant__ CUtensorMap map_w, const Params p)
 // come from shared memory (128 contiguous bytes per warp and pixel, conflict free).
 constexpr int kInTileBytes = HT * WT * 128;
 
-template <int ACT_POST>
-__global__ void __launch_bounds__(kDirectThreads, 3)
+// NBUF = 2: the next tile's copy is issued at the top of the iteration (three CTAs per SM);
+// NBUF = 1: one input buffer, refilled as soon as the depthwise phase has consumed it (the copy
+// then overlaps the MMA and the epilogue), which leaves room for four CTAs per SM.
+template <int ACT_POST, int NBUF>
+__global__ void __launch_bounds__(kDirectThreads, NBUF == 1 ? 4 : 3)
 sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
                           const __grid_constant__ CUtensorMap map_x, const Params p) {
   pdl_launch_dependents();
@@ -296,7 +299,7 @@ sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
   uint8_t* smem_a = smem;                                  // [128][64] halves, swizzled
   uint8_t* smem_b = smem_a + kAtomBytesA;                  // [npad][64] halves, swizzled
   uint8_t* smem_in = smem_b + p.b_atom_bytes;              // 2 x [HT][WT][64] halves, dense
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_in + 2 * kInTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_in + NBUF * kInTileBytes);
   const uint32_t w_bar = smem_u32(bars);
   const uint32_t mma_bar = smem_u32(bars + 1);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
@@ -359,7 +362,7 @@ sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
       // slot (it + 1) & 1 was last read in iteration it - 1, which ended with a CTA barrier
       const int tn = sched_next_tile(p.sched, p.total_tiles);
       next_tile_s[it & 1] = tn;
-      if (tn < p.total_tiles) fetch_tile(tn, (it + 1) & 1);
+      if (NBUF == 2 && tn < p.total_tiles) fetch_tile(tn, (it + 1) & 1);
     }
     const int tx_i = t % p.tiles_x;
     const int ty_i = (t / p.tiles_x) % p.tiles_y;
@@ -367,8 +370,8 @@ sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
     const int y0 = ty_i * TH, x0 = tx_i * TW;
 
     // ---- depthwise 3x3 from the shared-memory tile -> A tile -----------------------------------
-    mbar_wait(smem_u32(bars + 2 + (it & 1)), static_cast<uint32_t>(it >> 1) & 1u);
-    const uint32_t in_u32 = smem_u32(smem_in + (it & 1) * kInTileBytes);
+    mbar_wait(smem_u32(bars + 2 + (it % NBUF)), static_cast<uint32_t>(it / NBUF) & 1u);
+    const uint32_t in_u32 = smem_u32(smem_in + (it % NBUF) * kInTileBytes);
     for (int e = threadIdx.x; e < items; e += kDirectThreads) {
       const int xg = e / cp_count, cp = e - xg * cp_count;
       float2 wreg[9];
@@ -419,6 +422,10 @@ sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (NBUF == 1 && threadIdx.x == 0) {       // the input buffer is free again: prefetch the next tile
+      const int tn = next_tile_s[it & 1];
+      if (tn < p.total_tiles) fetch_tile(tn, 0);
+    }
     // ---- D = A * W^T ---------------------------------------------------------------------------
     if (threadIdx.x == 0) {
       if (!weights_ready) {
@@ -485,10 +492,10 @@ sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
   }
 }
 
-template <int POST>
+template <int POST, int NBUF>
 static int launch_direct_tma(const CUtensorMap& mw, const CUtensorMap& mx, const Params& p, int grid,
                              int smem_bytes, cudaStream_t stream) {
-  auto kern = sepconv_direct_tma_kernel<POST>;
+  auto kern = sepconv_direct_tma_kernel<POST, NBUF>;
   static int configured[kMaxDevices];
   if (int rc = ensure_dynamic_smem(kern, smem_bytes, configured)) return rc;
   EDET_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kDirectThreads), smem_bytes, stream, mw, mx, p));
@@ -556,14 +563,20 @@ extern "C" int edet_sepconv(const edet_fuse_input* h_inputs, int n_inputs, int p
     // c <= 64: the input tile comes through TMA, double buffered (sepconv_direct_tma_kernel)
     CUtensorMap mx;
     if (int rc = make_map4(&mx, p.fuse.in[0].ptr, c, wd, h, n, 64, WT, HT, /*swizzle=*/false)) return rc;
-    const int smem_tma = 1024 + kAtomBytesA + p.b_atom_bytes + 2 * kInTileBytes + 128;
+    const int nbuf = option_sepconv_impl() == 2 ? 1 : 2;
+    const int smem_tma = 1024 + kAtomBytesA + p.b_atom_bytes + nbuf * kInTileBytes + 128;
     int per = 232448 / (smem_tma + 1024);
     if (per * p.tmem_cols > 512) per = 512 / p.tmem_cols;
-    if (per > 3) per = 3;
+    if (per > (nbuf == 1 ? 4 : 3)) per = nbuf == 1 ? 4 : 3;
     const int grid_tma = p.total_tiles < per * sm_count ? p.total_tiles : per * sm_count;
-    if (post_act == EDET_ACT_SWISH) return launch_direct_tma<EDET_ACT_SWISH>(mw, mx, p, grid_tma, smem_tma, s);
-    if (post_act == EDET_ACT_RELU6) return launch_direct_tma<EDET_ACT_RELU6>(mw, mx, p, grid_tma, smem_tma, s);
-    if (post_act == EDET_ACT_NONE) return launch_direct_tma<EDET_ACT_NONE>(mw, mx, p, grid_tma, smem_tma, s);
+#define EDET_SEPC_TMA(POST)                                                                   \
+  if (post_act == POST)                                                                       \
+    return nbuf == 1 ? launch_direct_tma<POST, 1>(mw, mx, p, grid_tma, smem_tma, s)           \
+                     : launch_direct_tma<POST, 2>(mw, mx, p, grid_tma, smem_tma, s)
+    EDET_SEPC_TMA(EDET_ACT_SWISH);
+    EDET_SEPC_TMA(EDET_ACT_RELU6);
+    EDET_SEPC_TMA(EDET_ACT_NONE);
+#undef EDET_SEPC_TMA
     set_error("sepconv: unsupported activation %d", post_act);
     return EDET_ERR_UNSUPPORTED;
   }

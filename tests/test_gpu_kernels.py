@@ -438,13 +438,13 @@ SEP_CASES = [
 ]
 
 
-@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('impl', [0, 1, 2])
 @pytest.mark.parametrize('case', SEP_CASES)
 def test_sepconv(case, impl):
   """edet_sepconv (a head tower layer: depthwise 3x3 + pointwise in one kernel) == edet_fuse_dw +
   edet_pointwise_conv bit for bit (same fp16 rounding of the depthwise result), and both match
   the float64 restatement.  impl 0 / 1: input tile staged by TMA / loaded straight from global
-  memory."""
+  memory / staged by TMA in a single buffer (four CTAs per SM)."""
   ops = _ops()
   n, (h, w), c, nout, pre, post, modes = case
   ops.set_option('sepconv_impl', impl)
