@@ -24,7 +24,7 @@ struct Option {
 static Option g_options[] = {
     {"dw_impl", 0, 2, {0}},          // 0 auto (tiled kernel where eligible), 1 register kernel only
     {"stem_impl", 0, 1, {0}},        // 0 tensor-core stem, 1 CUDA-core stem
-    {"sepconv_impl", 0, 2, {0}},     // 0 TMA-staged input (2 buffers, 3 CTAs/SM), 1 loads from global, 2 TMA, 1 buffer, 4 CTAs/SM
+    {"sepconv_impl", 0, 2, {0}},     // 0 TMA-staged input (1 buffer, 4 CTAs/SM), 1 loads from global, 2 TMA, 2 buffers, 3 CTAs/SM
     {"pw_teams", 0, 3, {0}},         // 0 auto, 2 / 3 epilogue teams in pointwise_tc
     {"pw_smem_kb", 0, 113, {0}},     // 0 auto, else shared-memory budget of a pointwise_tc CTA
     {"persist_slack", 0, 148, {0}},  // CTAs a persistent kernel leaves out of its 2-per-SM grid

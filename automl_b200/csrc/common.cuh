@@ -174,7 +174,7 @@ inline cudaStream_t as_stream(edet_stream_t s) { return reinterpret_cast<cudaStr
 // Library options (edet_set_option): implementation switches for A/B measurements.
 int option_dw_impl();   // 0 auto (tiled kernel where eligible), 1 register kernel only, 2 = 0
 int option_stem_impl(); // 0 auto (tensor-core stem), 1 CUDA-core stem kernel
-int option_sepconv_impl();  // 0 auto (TMA-staged input for c <= 64), 1 loads straight from global
+int option_sepconv_impl();  // 0 auto (TMA-staged input for c <= 64, one buffer), 1 loads straight from global, 2 TMA double buffer
 int option_pw_teams();  // 0 auto, 2 / 3 = force that many epilogue teams in pointwise_tc
 int option_pw_smem_kb();     // 0 auto, else the shared-memory budget (KiB) of a pointwise_tc CTA
 int option_persist_slack();  // CTAs a persistent kernel leaves out of its two-per-SM grid (default 0)

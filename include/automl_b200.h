@@ -60,7 +60,8 @@ const char* edet_last_error(void);
  * for every setting).  Options: "dw_impl" = 0 (default: TMA-tiled depthwise kernel where eligible,
  * register-tiled kernel otherwise) | 1 (register-tiled kernel only); "pw_teams" = 0 (default:
  * three epilogue teams) | 2 | 3; "stem_impl" = 0 (default: tensor-core stem) | 1 (CUDA-core stem);
- * "sepconv_impl" = 0 (default: TMA-staged input tile for c <= 64) | 1 (loads from global);
+ * "sepconv_impl" = 0 (default: TMA-staged input tile for c <= 64, one buffer, four CTAs per SM) |
+ * 1 (loads from global) | 2 (TMA, two buffers, three CTAs per SM);
  * "pw_smem_kb" = 0 (default: 99 KiB per pointwise CTA where that keeps the TMA ring >= 4 deep, so
  * that one CTA shares an SM with an NMS CTA of the previous batch; else 113) | 64..113;
  * "persist_slack" = CTAs a persistent kernel leaves out of its two-per-SM grid (default 0). */

@@ -96,7 +96,8 @@ want = [('gpu__time_duration.sum', 'time'), ('dram__bytes_read.sum', 'dram rd'),
 labels = ['stem 640->320x32', 'blocks_1 fused expand+dw (mbconv_front)', 'head tower layer L3 (sepconv_direct)',
           'BiFPN node L3 (fuse_dw)', 'blocks_0 dw k3s1 320x32', 'blocks_1 dw k3s2 320x96', 'blocks_4 dw k5s1 80x240',
           'blocks_9 dw k5s1 40x672', 'blocks_1 expand 16->96', 'blocks_2 project 144->24 (+res, SE weights)',
-          'blocks_6 expand 80->480', 'blocks_12 project 1152->192', 'class-predict L3 64->810']
+          'blocks_6 expand 80->480', 'blocks_12 project 1152->192', 'class-predict L3 64->810 (logits stored: forward())',
+          'class head + arg-max L3 64->9x96 (detect path)']
 out = ['# ncu --set full summaries (round 2, final build)', '',
        '`ncu --set full --clock-control none -k regex:"stem_tc_kernel|fuse_dw_kernel|pointwise_tc|dw_tile_kernel|'
        'depthwise_kernel|sepconv|mbconv_front" python scripts/profile_kernels.py 1`',

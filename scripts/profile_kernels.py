@@ -87,6 +87,23 @@ pw(3276800, 16, 96, utils.ACT_SWISH)                 # blocks_1 expand
 pw(819200, 144, 24, utils.ACT_NONE, res=True, per_image=True)   # blocks_2 project
 pw(51200, 80, 480, utils.ACT_SWISH)                  # blocks_6 expand
 pw(12800, 1152, 192, utils.ACT_NONE, res=True, per_image=True)  # blocks_12 project
-pw(204800, 64, 810, utils.ACT_NONE)                  # class-predict L3
+pw(204800, 64, 810, utils.ACT_NONE)                  # class-predict L3 (forward(): logits stored)
+
+
+def class_argmax(h, f=64, a=9, c=90):
+  x = torch.randn(N, h, h, f, device=dev).half()
+  w = torch.zeros(a, ops.CLASS_ARGMAX_COLS, f, device=dev)
+  w[:, :c] = torch.randn(a, c, f, device=dev) / f**0.5
+  b = torch.full((a, ops.CLASS_ARGMAX_COLS), float('-inf'), device=dev)
+  b[:, :c] = -4.6
+  total = h * h * a
+  scores = torch.empty(N, total, device=dev)
+  classes = torch.empty(N, total, dtype=torch.int32, device=dev)
+  wp, bp = w.reshape(-1, f).half().contiguous(), b.reshape(-1).contiguous()
+  for _ in range(reps):
+    ops.class_argmax(x, wp, bp, scores, classes, 0, a)
+
+
+class_argmax(80)           # class head fused with the class arg-max, level 3 (detect path)
 torch.cuda.synchronize()
 print('done')

@@ -26,7 +26,9 @@ def main():
   last_block = max(i for i, n in enumerate(names) if n.startswith('blocks_'))
   first_head = min(i for i, n in enumerate(names) if n.startswith('class_net') or n.startswith('box_net'))
   cuts = [('stem..blocks', last_block + 1), ('+ feature network', first_head),
-          ('+ heads', eng.num_network_ops)]
+          ('+ heads', eng.num_network_ops), ('+ pre-NMS', len(names) - 1)]
+  # the launches of run(postprocess=True): class head fused with the class arg-max
+  eng._fused_target = eng._post[0] if eng.fuse_class_argmax else None  # pylint: disable=protected-access
   out, prev = [], 0.0
   for label, upto in cuts:
     fn = lambda upto=upto: eng._run_ops(upto)  # pylint: disable=protected-access
