@@ -550,8 +550,11 @@ class Engine(object):
     self._ev_nms = [torch.cuda.Event() for _ in range(2)]
     self._nms_pending = [False, False]
     # op list entries (set 0) for profiling / accounting
-    self._add('pre_nms', self._pre_ops[0], kind='pre_nms',
-              nbytes=2 * sum(t.numel() for t in cls_l + box_l) + 24 * n * K + 16 * K)
+    if self.fuse_class_argmax and topk == 0:   # boxes only: box logits in, decoded boxes out
+      pre_bytes = 2 * sum(t.numel() for t in box_l) + 16 * n * K + 16 * K
+    else:
+      pre_bytes = 2 * sum(t.numel() for t in cls_l + box_l) + 24 * n * K + 16 * K
+    self._add('pre_nms', self._pre_ops[0], kind='pre_nms', nbytes=pre_bytes)
     self._add('nms', self._nms_ops[0], kind='nms_v5', nbytes=28 * n * K, kernels=2)
     self.launches_per_forward = sum(i['kernels'] for i in self.op_info)
 
