@@ -194,41 +194,68 @@ depthwise_kernel(const __half* __restrict__ in, __half* __restrict__ out,
 //   hidden[n][j] = act(b1[j] + sum_c w1[j][c] * mean[c])
 // Also clears `zero_buf` (the squeeze accumulator the NEXT block will use).
 constexpr int kSeWarps = 8;
+// SE, first FC: hidden[img][j] = act(b1[j] + sum_c w1[j][c] * mean[img][c]).  `split` warps share
+// one output (each a contiguous slice of the channels; partial sums combined in warp order through
+// shared memory, so the result does not depend on timing): 1 when the batch alone fills the chip
+// (D0 at batch 32: 1536 outputs), up to 8 for small batches (D7x at batch 2: 320 outputs of 3840
+// channels each would otherwise be 40 CTAs walking 30 dependent iterations).
 __global__ void __launch_bounds__(kSeWarps * 32)
 se_fc1_kernel(const long long* __restrict__ se_sum, float inv_hw, const float* __restrict__ w1,
               const float* __restrict__ b1, float* __restrict__ hidden,
-              long long* __restrict__ zero_buf, long long zero_total, int n, int c, int se, int act) {
+              long long* __restrict__ zero_buf, long long zero_total, int n, int c, int se, int act,
+              int split) {
   pdl_launch_dependents();
   pdl_wait_prior();
+  __shared__ float part[kSeWarps];
   if (zero_buf != nullptr) {
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < zero_total;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
       zero_buf[i] = 0;
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * kSeWarps + warp;
-  if (unit >= n * se) return;
-  const int img = unit / se, j = unit - img * se;
-  const long long* sums = se_sum + static_cast<size_t>(img) * c;
-  const float* wr = w1 + static_cast<size_t>(j) * c;
-  const double scale = (1.0 / kSeFixedScale) * static_cast<double>(inv_hw);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int ch = lane;
-  for (; ch + 96 < c; ch += 128) {
-    const long long q0 = sums[ch], q1 = sums[ch + 32], q2 = sums[ch + 64], q3 = sums[ch + 96];
-    const float a0 = __ldg(wr + ch), a1 = __ldg(wr + ch + 32), a2 = __ldg(wr + ch + 64),
-                a3 = __ldg(wr + ch + 96);
-    s0 = fmaf(a0, static_cast<float>(static_cast<double>(q0) * scale), s0);
-    s1 = fmaf(a1, static_cast<float>(static_cast<double>(q1) * scale), s1);
-    s2 = fmaf(a2, static_cast<float>(static_cast<double>(q2) * scale), s2);
-    s3 = fmaf(a3, static_cast<float>(static_cast<double>(q3) * scale), s3);
-  }
-  for (; ch < c; ch += 32)
-    s0 = fmaf(__ldg(wr + ch), static_cast<float>(static_cast<double>(sums[ch]) * scale), s0);
-  float s = (s0 + s1) + (s2 + s3);
+  const int per_cta = kSeWarps / split;                     // outputs per CTA
+  const int unit = blockIdx.x * per_cta + warp / split;     // the warps of an output are adjacent
+  const int piece = warp % split;
+  const bool live = unit < n * se;
+  float s = 0.f;
+  int img = 0, j = 0;
+  if (live) {
+    img = unit / se;
+    j = unit - img * se;
+    const long long* sums = se_sum + static_cast<size_t>(img) * c;
+    const float* wr = w1 + static_cast<size_t>(j) * c;
+    const double scale = (1.0 / kSeFixedScale) * static_cast<double>(inv_hw);
+    // channel slice of this warp (multiples of 32 so the lanes stay aligned)
+    const int span = ((c + split * 32 - 1) / (split * 32)) * 32;
+    const int c_begin = piece * span, c_end = min(c, c_begin + span);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int ch = c_begin + lane;
+    for (; ch + 96 < c_end; ch += 128) {
+      const long long q0 = sums[ch], q1 = sums[ch + 32], q2 = sums[ch + 64], q3 = sums[ch + 96];
+      const float a0 = __ldg(wr + ch), a1 = __ldg(wr + ch + 32), a2 = __ldg(wr + ch + 64),
+                  a3 = __ldg(wr + ch + 96);
+      s0 = fmaf(a0, static_cast<float>(static_cast<double>(q0) * scale), s0);
+      s1 = fmaf(a1, static_cast<float>(static_cast<double>(q1) * scale), s1);
+      s2 = fmaf(a2, static_cast<float>(static_cast<double>(q2) * scale), s2);
+      s3 = fmaf(a3, static_cast<float>(static_cast<double>(q3) * scale), s3);
+    }
+    for (; ch < c_end; ch += 32)
+      s0 = fmaf(__ldg(wr + ch), static_cast<float>(static_cast<double>(sums[ch]) * scale), s0);
+    s = (s0 + s1) + (s2 + s3);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) hidden[static_cast<size_t>(img) * se + j] = apply_act(s + b1[j], act);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  }
+  if (split == 1) {
+    if (live && lane == 0) hidden[static_cast<size_t>(img) * se + j] = apply_act(s + b1[j], act);
+    return;
+  }
+  if (lane == 0) part[warp] = s;
+  __syncthreads();
+  if (live && piece == 0 && lane == 0) {
+    float t = 0.f;
+    for (int k = 0; k < split; ++k) t += part[warp + k];     // fixed order
+    hidden[static_cast<size_t>(img) * se + j] = apply_act(t + b1[j], act);
+  }
 }
 
 // SE, second FC + excitation folded into the project weights, one CTA per (128-channel slice,
@@ -360,10 +387,14 @@ extern "C" int edet_se_fc(const int64_t* se_sum, float inv_hw, const float* w1, 
   EDET_CHECK_ARG(!wt || (wt_scaled && nout > 0), "se_fc: wt given without wt_scaled/nout");
   const size_t smem = static_cast<size_t>(((se + 3) & ~3) + kSeSlice) * sizeof(float);
   EDET_CHECK_ARG(smem <= 48 * 1024, "se_fc: se too large");
-  EDET_CHECK_CUDA(launch_pdl(se_fc1_kernel, dim3(ceil_div(n * se, kSeWarps)), dim3(kSeWarps * 32),
-                             0, as_stream(stream), reinterpret_cast<const long long*>(se_sum),
-                             inv_hw, w1, b1, hidden, reinterpret_cast<long long*>(zero_buf),
-                             static_cast<long long>(n) * zero_count, n, c, se, act));
+  // warps per output: enough CTAs to cover the chip a few times, slices of >= 128 channels
+  int split = 1;
+  while (split < kSeWarps && n * se * split < 2048 && c / (2 * split) >= 128) split *= 2;
+  EDET_CHECK_CUDA(launch_pdl(se_fc1_kernel, dim3(ceil_div(n * se, kSeWarps / split)),
+                             dim3(kSeWarps * 32), 0, as_stream(stream),
+                             reinterpret_cast<const long long*>(se_sum), inv_hw, w1, b1, hidden,
+                             reinterpret_cast<long long*>(zero_buf),
+                             static_cast<long long>(n) * zero_count, n, c, se, act, split));
   EDET_CHECK_CUDA(launch_pdl(se_fc2_scale_kernel,
                              dim3(ceil_div(c, kSeSlice), n, wt ? ceil_div(nout, kSeRows) : 1), dim3(256), smem,
                              as_stream(stream), static_cast<const float*>(hidden), w2, b2, gate,

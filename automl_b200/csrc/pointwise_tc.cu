@@ -380,8 +380,12 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                static_cast<uint32_t>(as * p.block_n);
         const uint32_t bias_u32 = smem_bias_u32 + static_cast<uint32_t>(tc.n_blk * kArgmaxCols) * 4u;
-        float best = -CUDART_INF_F;
-        int best_c = 0;
+        // Running maximum over 32-bit keys (fp16 logit mapped to an order-preserving uint16) << 16 |
+        // (0xFFFF - column): one unsigned max per column pair gives the maximum AND its first
+        // column (equal logits: the lower column has the larger key), with no serial
+        // compare / select chain.  -0 is canonicalised to +0 first (the float compare of the
+        // stored-logits path treats them as equal).
+        uint32_t best_key = 0u;
 #pragma unroll
         for (int g = 0; g < kArgmaxCols / 16; ++g) {
           float v[16];
@@ -398,17 +402,32 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
             asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                 : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                 : "r"(bias_u32 + static_cast<uint32_t>(g * 16 + q * 4) * 4u));
-            const float bb[4] = {b.x, b.y, b.z, b.w};
+            const float2 s01 = __fadd2_rn(make_float2(v[q * 4 + 0], v[q * 4 + 1]), make_float2(b.x, b.y));
+            const float2 s23 = __fadd2_rn(make_float2(v[q * 4 + 2], v[q * 4 + 3]), make_float2(b.z, b.w));
+            const float2 pairs[2] = {s01, s23};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float x = __half2float(__float2half_rn(__fadd_rn(v[q * 4 + e], bb[e])));
-              if (x > best) {                    // strict: the first maximum wins, like tf.argmax
-                best = x;
-                best_c = g * 16 + q * 4 + e;
-              }
+            for (int e = 0; e < 2; ++e) {
+              // the two logits exactly as the storing epilogue rounds them; -0 -> +0
+              const __half2 h = __hadd2(__floats2half2_rn(pairs[e].x, pairs[e].y), __float2half2_rn(0.f));
+              const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+              uint32_t sgn;      // 0xFFFF in the halves that are negative
+              asm("prmt.b32 %0, %1, %2, 0xBB99;" : "=r"(sgn) : "r"(hb), "r"(0u));
+              const uint32_t ord = hb ^ (sgn | 0x80008000u);       // order-preserving uint16 x 2
+              // (0xFFFF - col) of the pair's two columns in one register; selectors as immediates
+              const uint32_t col = static_cast<uint32_t>(g * 16 + q * 4 + e * 2);
+              const uint32_t codes = ((0xFFFFu - (col + 1u)) << 16) | (0xFFFFu - col);
+              uint32_t k0, k1;
+              asm("prmt.b32 %0, %1, %2, 0x1054;" : "=r"(k0) : "r"(ord), "r"(codes));
+              asm("prmt.b32 %0, %1, %2, 0x3276;" : "=r"(k1) : "r"(ord), "r"(codes));
+              best_key = max(best_key, max(k0, k1));
             }
           }
         }
+        const uint32_t ord_best = best_key >> 16;
+        const unsigned short hbits = static_cast<unsigned short>(
+            (ord_best & 0x8000u) ? (ord_best ^ 0x8000u) : (~ord_best & 0xFFFFu));
+        const float best = __half2float(__ushort_as_half(hbits));
+        const int best_c = static_cast<int>(0xFFFFu - (best_key & 0xFFFFu));
         const int row = tc.m_blk * BLOCK_M + row_in_tile;
         if (row < p.rows) {
           const size_t o = static_cast<size_t>(tc.b) * p.am_total + p.am_anchor_begin +

@@ -266,14 +266,17 @@ def test_mbconv_expand_dw(case):
     assert torch.equal(again, se)
 
 
-@pytest.mark.parametrize('shape', [(3, 96, 4, 24), (2, 144, 6, 24), (2, 1152, 48, 320)])
+@pytest.mark.parametrize('shape', [(3, 96, 4, 24), (2, 144, 6, 24), (2, 1152, 48, 320),
+                                   (2, 3840, 160, 640),    # D7x at batch 2: 8 warps share an output
+                                   (2, 1000, 40, 64),      # ragged channel slices (4 warps)
+                                   (32, 672, 28, 112)])    # D0 batch 32: one warp per output
 def test_se_fc(shape):
   ops = _ops()
   n, c, se, nout = shape
   g = torch.Generator().manual_seed(5)
   sums = torch.randn(n, c, generator=g) * 20
   se_sum = torch.round(sums.double() * 2.0**20).to(torch.int64)
-  nxt = torch.full((n, 1160), 123, dtype=torch.int64, device=DEV)
+  nxt = torch.full((n, max(1160, c)), 123, dtype=torch.int64, device=DEV)
   w1, b1 = torch.randn(se, c, generator=g) * 2.0 / c**0.5, torch.randn(se, generator=g) * 0.1
   w2, b2 = torch.randn(c, se, generator=g) * 0.5, torch.randn(c, generator=g) * 0.1
   wt = torch.randn(nout, c, generator=g).half()
