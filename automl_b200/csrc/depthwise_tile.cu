@@ -86,7 +86,11 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * C::TILE_BYTES);      // [NSTAGE]
   unsigned long long* se_s = reinterpret_cast<unsigned long long*>(bars + NSTAGE);  // [2][kCB]
-  volatile int* unit_s = reinterpret_cast<volatile int*>(se_s + 2 * kCB);           // [NSTAGE]
+  // [NSTAGE] x {unit index, image, tile row, tile column}: decoded once by thread 0 (three integer
+  // divisions), read by everybody else with one 16-byte shared-memory load
+  volatile int4* unit_s = reinterpret_cast<volatile int4*>(
+      (reinterpret_cast<uintptr_t>(se_s + 2 * kCB) + 15) & ~static_cast<uintptr_t>(15));
+  int* unit_chunk_s = reinterpret_cast<int*>(const_cast<int4*>(unit_s) + NSTAGE);      // [NSTAGE]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -97,8 +101,15 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
   if (HAS_SE && threadIdx.x < 2 * kCB) se_s[threadIdx.x] = 0ull;
   pdl_wait_prior();      // everything above overlapped the previous kernel's tail
 
-  auto issue = [&](int u, int stage) {       // thread 0 only
-    const Unit un = decode(u, p);
+  auto park = [&](int u, int stage) -> Unit {   // thread 0 only: publish the unit of a stage
+    Unit un;
+    un.n = un.ty = un.tx = un.chunk = 0;
+    if (u < p.total_units) un = decode(u, p);
+    unit_chunk_s[stage] = un.chunk;
+    const_cast<int4*>(unit_s)[stage] = make_int4(u, un.n, un.ty, un.tx);
+    return un;
+  };
+  auto issue = [&](const Unit& un, int stage) {       // thread 0 only
     const uint32_t bar = smem_u32(&bars[stage]);
     mbar_expect_tx(bar, static_cast<uint32_t>(C::TIH * C::TIW * kPixBytes));
     tma_load_4d(smem_u32(smem + stage * C::TILE_BYTES), &map_x, bar, un.chunk * kCB,
@@ -118,8 +129,8 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       const int u = s == 0 ? static_cast<int>(blockIdx.x) : next_unit();
-      unit_s[s] = u;
-      if (u < p.total_units) issue(u, s);
+      const Unit un = park(u, s);
+      if (u < p.total_units) issue(un, s);
     }
   }
   __syncthreads();
@@ -136,10 +147,11 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
 
   for (int it = 0;; ++it) {
     const int stage = it % NSTAGE;
-    const int u = unit_s[stage];
-    if (u >= p.total_units) break;       // same value for every thread of the CTA
+    const int4 ui = const_cast<const int4*>(unit_s)[stage];
+    if (ui.x >= p.total_units) break;       // same value for every thread of the CTA
     const uint32_t phase = static_cast<uint32_t>(it / NSTAGE) & 1u;
-    const Unit un = decode(u, p);
+    Unit un;
+    un.n = ui.y; un.ty = ui.z; un.tx = ui.w; un.chunk = unit_chunk_s[stage];
     const int cp = un.chunk * (kCB / 2) + lane;                  // channel pair of this lane
     const bool lane_ok = cp < cp_total;
     if (un.chunk != cur_chunk) {                                 // (re)load this slice's weights
@@ -213,9 +225,9 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
     }
     __syncthreads();       // every thread has finished reading this stage (and adding to se_unit)
     if (threadIdx.x == 0) {
-      const int un_next = next_unit();
-      unit_s[stage] = un_next;           // read NSTAGE iterations (>= 1 barrier) later
-      if (un_next < p.total_units) issue(un_next, stage);
+      const int u_next = next_unit();
+      const Unit un_next = park(u_next, stage);   // read NSTAGE iterations (>= 1 barrier) later
+      if (u_next < p.total_units) issue(un_next, stage);
     }
     if (HAS_SE && threadIdx.x < kCB) {
       // flush this unit's sums; the OTHER buffer takes the next unit's atomics meanwhile, and
@@ -232,7 +244,8 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
 template <int K, int S>
 static int launch_kernel(const CUtensorMap& mx, const Params& p, int grid, int act, cudaStream_t stream) {
   using C = Cfg<K, S>;
-  const int smem_bytes = 1024 + C::NSTAGE * C::TILE_BYTES + C::NSTAGE * 8 + 2 * kCB * 8 + 32;
+  const int smem_bytes = 1024 + C::NSTAGE * C::TILE_BYTES + C::NSTAGE * 8 + 2 * kCB * 8 + 16 +
+                         C::NSTAGE * 20 + 16;
   const bool hb = p.bias != nullptr, hs = p.se_sum != nullptr;
 #define EDET_DWT(ACT, HB, HS)                                                                  \
   do {                                                                                         \

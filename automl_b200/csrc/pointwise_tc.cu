@@ -72,6 +72,15 @@ constexpr int kArgmaxCols = 96;   // columns per anchor in the padded class-head
 struct TileCoord {
   int b, m_blk, n_blk;
 };
+// (accumulator stage, mbarrier phase) of consecutive tiles without a division per tile
+struct StageCounter {
+  int as = -1;
+  uint32_t phase = 1u;
+  __device__ __forceinline__ void next(int stages) {
+    if (++as == stages) as = 0;
+    if (as == 0) phase ^= 1u;
+  }
+};
 // Biases of 8 consecutive output columns from the copy of the (zero-padded) bias vector that the
 // prologue stages in shared memory: two ld.shared.v4 instead of two global loads plus the
 // ragged-edge branches in the middle of the MUFU / issue-bound epilogue.
@@ -87,10 +96,17 @@ __device__ __forceinline__ void load_bias8(uint32_t smem_bias_u32, int col, floa
 
 __device__ __forceinline__ TileCoord decode_tile(int t, const Params& p) {
   TileCoord c;
-  c.n_blk = t % p.num_n_blocks;
-  t /= p.num_n_blocks;
-  c.m_blk = t % p.num_m_blocks;
-  c.b = t / p.num_m_blocks;
+  c.n_blk = 0;
+  if (p.num_n_blocks != 1) {       // (uniform) most layers are one N tile wide ...
+    c.n_blk = t % p.num_n_blocks;
+    t /= p.num_n_blocks;
+  }
+  c.m_blk = t;
+  c.b = 0;
+  if (p.batch != 1) {              // ... and one batch entry long: no division at all
+    c.m_blk = t % p.num_m_blocks;
+    c.b = t / p.num_m_blocks;
+  }
   return c;
 }
 
@@ -219,10 +235,12 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                              (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
+      StageCounter sc;
       for (int iter = 0;; ++iter) {
         if (ring_get(iter, false) >= p.total_tiles) break;
-        const int as = iter % p.accum_stages;
-        const uint32_t aphase = static_cast<uint32_t>(iter / p.accum_stages) & 1u;
+        sc.next(p.accum_stages);
+        const int as = sc.as;
+        const uint32_t aphase = sc.phase;
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * p.block_n);
@@ -261,12 +279,14 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
     const int row_in_tile = quarter * 32 + lane;
     uint8_t* my_slabs = smem_store + e_warp * p.slabs_per_warp * (32 * 128);
     int store_cnt = 0;
+    StageCounter sc;
     for (int iter = 0;; ++iter) {
       const int t = ring_get(iter, true);
       if (t >= p.total_tiles) break;
       const TileCoord tc = decode_tile(t, p);
-      const int as = iter % p.accum_stages;
-      const uint32_t aphase = static_cast<uint32_t>(iter / p.accum_stages) & 1u;
+      sc.next(p.accum_stages);
+      const int as = sc.as;
+      const uint32_t aphase = sc.phase;
       const int n0 = tc.n_blk * p.block_n;
       const int row = tc.m_blk * BLOCK_M + row_in_tile;
       const bool row_ok = row < p.rows;
@@ -363,15 +383,19 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       const int quarter = warp & 3;
       const int team = e_warp >> 2;
       const int row_in_tile = quarter * 32 + lane;
+      StageCounter sc;
+      int rot = TEAMS - 1;                      // iter % TEAMS, kept incrementally
       for (int iter = 0;; ++iter) {
         const int t = ring_get(iter, true);
         if (t >= p.total_tiles) break;
         const TileCoord tc = decode_tile(t, p);
-        const int as = iter % p.accum_stages;
-        const uint32_t aphase = static_cast<uint32_t>(iter / p.accum_stages) & 1u;
+        sc.next(p.accum_stages);
+        if (++rot == TEAMS) rot = 0;
+        const int as = sc.as;
+        const uint32_t aphase = sc.phase;
         mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
         tc_fence_after();
-        if (iter % TEAMS != team) {              // not this team's tile: hand the accumulator back
+        if (rot != team) {                       // not this team's tile: hand the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
@@ -447,12 +471,16 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       const int row_in_tile = quarter * 32 + lane;
       uint8_t* my_slabs = smem_store + e_warp * p.slabs_per_warp * kSlabBytes;
       int store_cnt = 0;
+      StageCounter sc;
+      int rot = TEAMS - 1;                      // iter % TEAMS, kept incrementally
       for (int iter = 0;; ++iter) {
         const int t = ring_get(iter, true);
         if (t >= p.total_tiles) break;
         const TileCoord tc = decode_tile(t, p);
-        const int as = iter % p.accum_stages;
-        const uint32_t aphase = static_cast<uint32_t>(iter / p.accum_stages) & 1u;
+        sc.next(p.accum_stages);
+        if (++rot == TEAMS) rot = 0;
+        const int as = sc.as;
+        const uint32_t aphase = sc.phase;
         const int n0 = tc.n_blk * p.block_n;
         const int row = tc.m_blk * BLOCK_M + row_in_tile;
         const bool row_ok = row < p.rows;
@@ -467,7 +495,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
         // unit u of tile `iter` belongs to team (u + iter) % TEAMS: thin layers (one or two units
         // per tile) keep all three teams busy on consecutive tiles (up to kMaxAccum accumulators
         // in flight) instead of leaving two of them idle
-        const int u_first = (team + TEAMS - iter % TEAMS) % TEAMS;
+        const int u_first = team >= rot ? team - rot : team + TEAMS - rot;
         int my_last = -1;
         for (int u = u_first; u < num_units; u += TEAMS) my_last = u;
         if (my_last < 0) {
