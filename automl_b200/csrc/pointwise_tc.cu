@@ -138,7 +138,9 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
   uint64_t* ring_full = bars + 2 * kMaxStages + 2 * kMaxAccum;   // [kRing] producer -> consumers
   uint64_t* ring_empty = ring_full + kRing;              // [kRing] consumers -> producer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring_empty + kRing);
-  volatile int* tile_ring = reinterpret_cast<volatile int*>(tmem_slot + 4);   // [kRing]
+  // [kRing] x {tile, batch entry, M block, N block}: the producer decodes each tile once (its two
+  // integer divisions) and the 13 consumer warps read the coordinates with one 16-byte load
+  volatile int4* tile_ring = reinterpret_cast<volatile int4*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -179,13 +181,18 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
   pdl_wait_prior();          // everything above overlapped the previous kernel's tail
 
   // consumer side of the tile ring: whole warp (or the single MMA lane) waits, reads, releases
-  auto ring_get = [&](int i, bool whole_warp) -> int {
+  auto ring_get = [&](int i, bool whole_warp, TileCoord* tc) -> int {
     const int slot = i & (kRing - 1);
     mbar_wait(smem_u32(&ring_full[slot]), static_cast<uint32_t>(i / kRing) & 1u);
-    const int t = tile_ring[slot];
+    const int4 e = const_cast<const int4*>(tile_ring)[slot];
     if (whole_warp) __syncwarp();
     if (!whole_warp || lane == 0) mbar_arrive(smem_u32(&ring_empty[slot]));
-    return t;
+    if (tc) {
+      tc->b = e.y;
+      tc->m_blk = e.z;
+      tc->n_blk = e.w;
+    }
+    return e.x;
   };
 
   if (warp == 0) {
@@ -206,10 +213,12 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
         }
         const int slot = i & (kRing - 1);
         mbar_wait(smem_u32(&ring_empty[slot]), (static_cast<uint32_t>(i / kRing) & 1u) ^ 1u);
-        tile_ring[slot] = t;
-        mbar_arrive(smem_u32(&ring_full[slot]));     // release: the index is visible to waiters
+        TileCoord tc;
+        tc.b = tc.m_blk = tc.n_blk = 0;
+        if (t < p.total_tiles) tc = decode_tile(t, p);
+        const_cast<int4*>(tile_ring)[slot] = make_int4(t, tc.b, tc.m_blk, tc.n_blk);
+        mbar_arrive(smem_u32(&ring_full[slot]));     // release: the entry is visible to waiters
         if (t >= p.total_tiles) break;
-        const TileCoord tc = decode_tile(t, p);
         const int wb = (p.wbatch > 1) ? tc.b : 0;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
@@ -237,7 +246,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       uint32_t phase = 0;
       StageCounter sc;
       for (int iter = 0;; ++iter) {
-        if (ring_get(iter, false) >= p.total_tiles) break;
+        if (ring_get(iter, false, nullptr) >= p.total_tiles) break;
         sc.next(p.accum_stages);
         const int as = sc.as;
         const uint32_t aphase = sc.phase;
@@ -281,9 +290,9 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
     int store_cnt = 0;
     StageCounter sc;
     for (int iter = 0;; ++iter) {
-      const int t = ring_get(iter, true);
+      TileCoord tc;
+      const int t = ring_get(iter, true, &tc);
       if (t >= p.total_tiles) break;
-      const TileCoord tc = decode_tile(t, p);
       sc.next(p.accum_stages);
       const int as = sc.as;
       const uint32_t aphase = sc.phase;
@@ -386,9 +395,9 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       StageCounter sc;
       int rot = TEAMS - 1;                      // iter % TEAMS, kept incrementally
       for (int iter = 0;; ++iter) {
-        const int t = ring_get(iter, true);
+        TileCoord tc;
+        const int t = ring_get(iter, true, &tc);
         if (t >= p.total_tiles) break;
-        const TileCoord tc = decode_tile(t, p);
         sc.next(p.accum_stages);
         if (++rot == TEAMS) rot = 0;
         const int as = sc.as;
@@ -474,9 +483,9 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a,
       StageCounter sc;
       int rot = TEAMS - 1;                      // iter % TEAMS, kept incrementally
       for (int iter = 0;; ++iter) {
-        const int t = ring_get(iter, true);
+        TileCoord tc;
+        const int t = ring_get(iter, true, &tc);
         if (t >= p.total_tiles) break;
-        const TileCoord tc = decode_tile(t, p);
         sc.next(p.accum_stages);
         if (++rot == TEAMS) rot = 0;
         const int as = sc.as;
@@ -660,7 +669,7 @@ int run(const __half* a, int lda, const __half* wt, int wbatch, const float* bia
   const int bias_cols = p.num_n_blocks * p.block_n;
   EDET_CHECK_ARG(bias_cols <= kMaxBiasSmem, "pointwise_tc: nout %d too wide", nout);
   p.bias_floats = bias_cols;
-  const int ctrl = p.bias_floats * 4 + (2 * kMaxStages + 2 * kMaxAccum + 2 * kRing) * 8 + 16 + 4 * kRing;
+  const int ctrl = p.bias_floats * 4 + (2 * kMaxStages + 2 * kMaxAccum + 2 * kRing) * 8 + 16 + 16 * kRing;
   int best_stages = 0, fixed = 0, stage_bytes = 0;
   auto plan = [&](int limit) {
     best_stages = 0;

@@ -304,7 +304,9 @@ sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
   const uint32_t w_bar = smem_u32(bars);
   const uint32_t mma_bar = smem_u32(bars + 1);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  volatile int* next_tile_s = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [2]
+  // [2] x {tile, image, tile row, tile column}: thread 0 decodes the next tile (its divisions)
+  // when it fetches it; everybody reads the coordinates with one 16-byte load
+  volatile int4* next_tile_s = reinterpret_cast<volatile int4*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -341,13 +343,16 @@ sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
   const float2* w2 = reinterpret_cast<const float2*>(p.dw_w);
   pdl_wait_prior();
 
-  auto fetch_tile = [&](int tile, int slot) {          // thread 0 only
+  auto decode = [&](int tile) -> int4 {                // {tile, image, tile row, tile column}
+    if (tile >= p.total_tiles) return make_int4(tile, 0, 0, 0);
     const int tx_i = tile % p.tiles_x;
-    const int ty_i = (tile / p.tiles_x) % p.tiles_y;
-    const int n = tile / (p.tiles_x * p.tiles_y);
+    const int rest = tile / p.tiles_x;
+    return make_int4(tile, rest / p.tiles_y, rest % p.tiles_y, tx_i);
+  };
+  auto fetch_tile = [&](const int4& tc, int slot) {    // thread 0 only
     const uint32_t bar = smem_u32(bars + 2 + slot);
     mbar_expect_tx(bar, static_cast<uint32_t>(kInTileBytes));
-    tma_load_4d(smem_u32(smem_in + slot * kInTileBytes), &map_x, bar, 0, tx_i * TW - 1, ty_i * TH - 1, n);
+    tma_load_4d(smem_u32(smem_in + slot * kInTileBytes), &map_x, bar, 0, tc.w * TW - 1, tc.z * TH - 1, tc.y);
   };
 
   const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(p.npad >> 3) << 17) |
@@ -356,19 +361,17 @@ sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
   uint32_t mma_phase = 0;
   bool weights_ready = false;
 
-  int t = blockIdx.x;
-  if (threadIdx.x == 0 && t < p.total_tiles) fetch_tile(t, 0);
-  for (int it = 0; t < p.total_tiles; ++it) {
+  int4 cur = decode(blockIdx.x);
+  if (threadIdx.x == 0 && cur.x < p.total_tiles) fetch_tile(cur, 0);
+  for (int it = 0; cur.x < p.total_tiles; ++it) {
     if (threadIdx.x == 0) {
       // slot (it + 1) & 1 was last read in iteration it - 1, which ended with a CTA barrier
-      const int tn = sched_next_tile(p.sched, p.total_tiles);
-      next_tile_s[it & 1] = tn;
-      if (NBUF == 2 && tn < p.total_tiles) fetch_tile(tn, (it + 1) & 1);
+      const int4 nx = decode(sched_next_tile(p.sched, p.total_tiles));
+      const_cast<int4*>(next_tile_s)[it & 1] = nx;
+      if (NBUF == 2 && nx.x < p.total_tiles) fetch_tile(nx, (it + 1) & 1);
     }
-    const int tx_i = t % p.tiles_x;
-    const int ty_i = (t / p.tiles_x) % p.tiles_y;
-    const int n = t / (p.tiles_x * p.tiles_y);
-    const int y0 = ty_i * TH, x0 = tx_i * TW;
+    const int n = cur.y;
+    const int y0 = cur.z * TH, x0 = cur.w * TW;
 
     // ---- depthwise 3x3 from the shared-memory tile -> A tile -----------------------------------
     mbar_wait(smem_u32(bars + 2 + (it % NBUF)), static_cast<uint32_t>(it / NBUF) & 1u);
@@ -424,8 +427,8 @@ sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
     tc_fence_before();
     __syncthreads();
     if (NBUF == 1 && threadIdx.x == 0) {       // the input buffer is free again: prefetch the next tile
-      const int tn = next_tile_s[it & 1];
-      if (tn < p.total_tiles) fetch_tile(tn, 0);
+      const int4 nx = const_cast<const int4*>(next_tile_s)[it & 1];
+      if (nx.x < p.total_tiles) fetch_tile(nx, 0);
     }
     // ---- D = A * W^T ---------------------------------------------------------------------------
     if (threadIdx.x == 0) {
@@ -478,7 +481,7 @@ sepconv_direct_tma_kernel(const __grid_constant__ CUtensorMap map_w,
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    t = next_tile_s[it & 1];
+    cur = const_cast<const int4*>(next_tile_s)[it & 1];
   }
 
   if (threadIdx.x == 0 && !weights_ready) mbar_wait(w_bar, 0);

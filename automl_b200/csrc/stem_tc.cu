@@ -73,7 +73,10 @@ stem_tc_kernel(const Params p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(in_s + 2 * kInPad);
   const uint32_t mma_bar = smem_u32(bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
-  volatile int* next_tile_s = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [2]
+  // [2] x {tile, image, tile row, tile column}: thread 0 decodes the next tile once (the integer
+  // divisions); everybody reads the coordinates with one 16-byte load
+  volatile int4* next_tile_s = reinterpret_cast<volatile int4*>(
+      (reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~static_cast<uintptr_t>(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -115,10 +118,13 @@ stem_tc_kernel(const Params p) {
   // The input patch of the NEXT tile is fetched with cp.async (4-byte copies, zero fill outside the
   // image) into the other half of a double buffer while the current tile is converted, multiplied
   // and written out, so its global-memory latency is off the critical path.
-  auto fetch_patch = [&](int tile, int slot) {
-    const int tx_i = tile % p.tiles_x;
-    const int ty_i = (tile / p.tiles_x) % p.tiles_y;
-    const int n = tile / (p.tiles_x * p.tiles_y);
+  auto decode = [&](int tile) -> int4 {              // {tile, image, tile row, tile column}
+    if (tile >= p.total_tiles) return make_int4(tile, 0, 0, 0);
+    const int rest = tile / p.tiles_x;
+    return make_int4(tile, rest / p.tiles_y, rest % p.tiles_y, tile % p.tiles_x);
+  };
+  auto fetch_patch = [&](const int4& tc, int slot) {
+    const int tx_i = tc.w, ty_i = tc.z, n = tc.y;
     const int iy0 = ty_i * TH * 2 - p.pad_t;
     const int xf0 = (tx_i * TW * 2 - p.pad_l) * 3;     // first float of the patch inside an image row
     const float* img = p.in + static_cast<size_t>(n) * p.h * row_floats;
@@ -135,20 +141,19 @@ stem_tc_kernel(const Params p) {
     cp_async_commit();
   };
 
-  int t = blockIdx.x;
-  if (t < p.total_tiles) fetch_patch(t, 0);
-  for (int it = 0; t < p.total_tiles; ++it) {
-    if (threadIdx.x == 0) next_tile_s[it & 1] = sched_next_tile(p.sched, p.total_tiles);
-    const int tx_i = t % p.tiles_x;
-    const int ty_i = (t / p.tiles_x) % p.tiles_y;
-    const int n = t / (p.tiles_x * p.tiles_y);
-    const int y0 = ty_i * TH, x0 = tx_i * TW;
+  int4 cur = decode(blockIdx.x);
+  if (cur.x < p.total_tiles) fetch_patch(cur, 0);
+  for (int it = 0; cur.x < p.total_tiles; ++it) {
+    if (threadIdx.x == 0)
+      const_cast<int4*>(next_tile_s)[it & 1] = decode(sched_next_tile(p.sched, p.total_tiles));
+    const int n = cur.y;
+    const int y0 = cur.z * TH, x0 = cur.w * TW;
 
     // ---- 1. this tile's patch has landed; start fetching the next tile's ------------------------
     cp_async_wait_all();
     __syncthreads();                                   // patch + next_tile_s visible to everyone
-    const int t_next = next_tile_s[it & 1];
-    if (t_next < p.total_tiles) fetch_patch(t_next, (it + 1) & 1);
+    const int4 nxt = const_cast<const int4*>(next_tile_s)[it & 1];
+    if (nxt.x < p.total_tiles) fetch_patch(nxt, (it + 1) & 1);
     const uint32_t patch_u32 = in_u32 + (it & 1) * kInPad * 4;
     // ---- 2. A row m: 27 hi halves, 27 lo halves, 10 zeros -> 8 swizzled 16-byte pieces ----------
     {
@@ -227,7 +232,7 @@ stem_tc_kernel(const Params p) {
     tc_fence_before();
     __syncthreads();       // TMEM, A and the input patch are free for the next tile
     tc_fence_after();
-    t = t_next;
+    cur = nxt;
   }
 
   tc_fence_before();
@@ -271,7 +276,7 @@ int run(const float* in, __half* out, const __half* w, const float* bias, int n,
   if (!p.sched) return EDET_ERR_CUDA;
   const int sms = device_sm_count();
   if (!sms) return EDET_ERR_CUDA;
-  const int smem_bytes = 1024 + kABytes + kBBytes + 2 * kInPad * 4 + 64;
+  const int smem_bytes = 1024 + kABytes + kBBytes + 2 * kInPad * 4 + 96;
   int per_sm = 232448 / (smem_bytes + 1024);
   if (per_sm > 6) per_sm = 6;
   if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;
