@@ -26,6 +26,7 @@ namespace dwt {
 using namespace pwtc;
 
 constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
 constexpr int kCB = 64;                 // channels per work unit (one 128-byte pixel row in smem)
 constexpr int kPixBytes = kCB * 2;
 
@@ -85,11 +86,15 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * C::TILE_BYTES);      // [NSTAGE]
-  unsigned long long* se_s = reinterpret_cast<unsigned long long*>(bars + NSTAGE);  // [2][kCB]
+  // SE squeeze partials [2][warps][kCB]: every warp parks the fixed-point sums of its lanes'
+  // channel pairs with plain stores; after the unit's barrier 64 threads add the eight warps up and
+  // issue the global atomics (64-bit shared-memory atomics are CAS loops, 8-way contended here)
+  unsigned long long* se_s = reinterpret_cast<unsigned long long*>(
+      (reinterpret_cast<uintptr_t>(bars + NSTAGE) + 15) & ~static_cast<uintptr_t>(15));
   // [NSTAGE] x {unit index, image, tile row, tile column}: decoded once by thread 0 (three integer
   // divisions), read by everybody else with one 16-byte shared-memory load
   volatile int4* unit_s = reinterpret_cast<volatile int4*>(
-      (reinterpret_cast<uintptr_t>(se_s + 2 * kCB) + 15) & ~static_cast<uintptr_t>(15));
+      (reinterpret_cast<uintptr_t>(se_s + 2 * kWarps * kCB) + 15) & ~static_cast<uintptr_t>(15));
   int* unit_chunk_s = reinterpret_cast<int*>(const_cast<int4*>(unit_s) + NSTAGE);      // [NSTAGE]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -98,7 +103,6 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
   }
-  if (HAS_SE && threadIdx.x < 2 * kCB) se_s[threadIdx.x] = 0ull;
   pdl_wait_prior();      // everything above overlapped the previous kernel's tail
 
   auto park = [&](int u, int stage) -> Unit {   // thread 0 only: publish the unit of a stage
@@ -217,11 +221,12 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
         orow += static_cast<size_t>(p.wo) * cp_total;
       }
     }
-    unsigned long long* se_unit = se_s + (it & 1) * kCB;
-    if (HAS_SE && lane_ok) {
-      // 2^-20 fixed point, integer atomics: order independent => bit-reproducible squeeze
-      atomicAdd(&se_unit[2 * lane], static_cast<unsigned long long>(__float2ll_rn(ssum.x * 1048576.f)));
-      atomicAdd(&se_unit[2 * lane + 1], static_cast<unsigned long long>(__float2ll_rn(ssum.y * 1048576.f)));
+    unsigned long long* se_unit = se_s + (it & 1) * (kWarps * kCB);
+    if (HAS_SE) {
+      // 2^-20 fixed point, integer sums: order independent => bit-reproducible squeeze
+      const unsigned long long sx = lane_ok ? static_cast<unsigned long long>(__float2ll_rn(ssum.x * 1048576.f)) : 0ull;
+      const unsigned long long sy = lane_ok ? static_cast<unsigned long long>(__float2ll_rn(ssum.y * 1048576.f)) : 0ull;
+      *reinterpret_cast<ulonglong2*>(se_unit + warp * kCB + 2 * lane) = make_ulonglong2(sx, sy);
     }
     __syncthreads();       // every thread has finished reading this stage (and adding to se_unit)
     if (threadIdx.x == 0) {
@@ -230,13 +235,13 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
       if (u_next < p.total_units) issue(un_next, stage);
     }
     if (HAS_SE && threadIdx.x < kCB) {
-      // flush this unit's sums; the OTHER buffer takes the next unit's atomics meanwhile, and
-      // this one is zeroed again before the barrier that precedes its next use
+      // flush this unit's sums; the OTHER buffer takes the next unit's partials meanwhile
       const int ch = un.chunk * kCB + threadIdx.x;
-      const unsigned long long v = se_unit[threadIdx.x];
+      unsigned long long v = 0ull;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) v += se_unit[w * kCB + threadIdx.x];
       if (ch < p.c && v != 0ull)
         atomicAdd(reinterpret_cast<unsigned long long*>(p.se_sum) + static_cast<size_t>(un.n) * p.c + ch, v);
-      se_unit[threadIdx.x] = 0ull;
     }
   }
 }
@@ -244,7 +249,7 @@ dw_tile_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
 template <int K, int S>
 static int launch_kernel(const CUtensorMap& mx, const Params& p, int grid, int act, cudaStream_t stream) {
   using C = Cfg<K, S>;
-  const int smem_bytes = 1024 + C::NSTAGE * C::TILE_BYTES + C::NSTAGE * 8 + 2 * kCB * 8 + 16 +
+  const int smem_bytes = 1024 + C::NSTAGE * C::TILE_BYTES + C::NSTAGE * 8 + 2 * kWarps * kCB * 8 + 16 +
                          C::NSTAGE * 20 + 16;
   const bool hb = p.bias != nullptr, hs = p.se_sum != nullptr;
 #define EDET_DWT(ACT, HB, HS)                                                                  \
