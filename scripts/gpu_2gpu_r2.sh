@@ -1,4 +1,4 @@
-# Round 2, call K (2 GPUs): the N > 1 path of bench.py exactly as the driver launches it.
+# Round 2, 2 GPUs: the N > 1 path of bench.py exactly as the driver launches it.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -1
