@@ -4,7 +4,9 @@
     casts weights to fp16 / biases to fp32 and uploads them once;
   * allocates every activation buffer once (NHWC fp16, static shapes);
   * records the launch list (stem -> MBConv blocks -> extra levels -> BiFPN cells -> heads ->
-    pre-NMS -> NMS) and replays it, optionally as one CUDA graph.
+    pre-NMS -> NMS) and replays it as CUDA graphs: the whole network as one graph for forward(),
+    three overlapping stages on three streams for run(postprocess=True) (backbone of step i+1 over
+    feature network + heads + pre-NMS of step i over NMS of step i; Engine._run_pipelined).
 
 The launch list mirrors the call structure of efficientdet_arch.efficientdet
 (/root/reference/efficientdet/efficientdet_arch.py:547-577) and inference.det_post_process
@@ -639,11 +641,13 @@ class Engine(object):
   def run(self, postprocess=True, after_nms=None):
     """Enqueues one forward from self.input.
 
-    postprocess=False: network only, on the current stream.
-    postprocess=True : network + pre-NMS on the current stream, then NMS (and `after_nms(dets)`,
-      e.g. the all-gather / D2H copy) on the engine's NMS stream, so consecutive steps overlap the
-      NMS of step i with the network of step i+1.  Call wait_detections() (or detect()) before
-      reading `self.detections` from the current stream.
+    postprocess=False: network only, on the current stream (writes every head output).
+    postprocess=True : backbone on the current stream, feature network + heads + pre-NMS on the
+      engine's head stream, NMS (and `after_nms(dets)`, e.g. the all-gather / D2H copy) on its NMS
+      stream, so consecutive steps overlap (pipeline=False: network + pre-NMS as one graph on the
+      current stream, only the NMS overlaps the next step).  The class logits are not stored on
+      this path (fuse_class_argmax).  Call wait_detections() (or detect()) before reading
+      `self.detections` from the current stream.
     """
     net_upto = self.num_network_ops
     if not postprocess:
