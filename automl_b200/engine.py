@@ -546,9 +546,6 @@ class Engine(object):
     self._head_capture_stream = torch.cuda.Stream(device=self.device, priority=self._head_priority)
     self._ev_bb = torch.cuda.Event()
     self._ev_early = torch.cuda.Event()
-    # recorded once the step no longer reads self.input (after the stem's graph): the next request's
-    # pre-process may overwrite it from another stream (ServingDriver)
-    self.input_free = torch.cuda.Event()
     self._ev_head = torch.cuda.Event()
     self._head_pending = False
     self._ev_pre = [torch.cuda.Event() for _ in range(2)]
@@ -662,7 +659,6 @@ class Engine(object):
         self._graph_for('net', lambda: self._run_ops(net_upto)).replay()
       else:
         self._run_ops(net_upto)
-      self.input_free.record(torch.cuda.current_stream(self.device))
       return
     sidx = self._step % 2
     ring = self._step % 4
@@ -685,7 +681,6 @@ class Engine(object):
         self._graph_for(('net+pre', sidx), net_and_pre).replay()
       else:
         net_and_pre()
-      self.input_free.record(main)
       self._ev_pre[sidx].record(main)
       self._enqueue_nms(sidx, after_nms, ring)
     self._cur = sidx
@@ -738,7 +733,6 @@ class Engine(object):
         for sx in (0, 1):
           (self._pre_ops_full[sx] if self._pre_ops_full else self._pre_ops[sx])()
     self._replay('bb1', lambda: self._run_ops(split))
-    self.input_free.record(main)
     if self.defer_heads:
       self._ev_early.record(main)
       self.flush(after=self._ev_early)          # head + NMS stages of the previous step

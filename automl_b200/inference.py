@@ -203,7 +203,7 @@ class ServingDriver(object):
   # ---- serving -------------------------------------------------------------------------------
   def _stage_raw(self, eng, slot, image_arrays):
     """Uploads the uint8 images (copy stream, from pinned memory) and runs the device pre-process
-    into the engine input (copy stream too; the current stream waits for it)."""
+    into the engine input (current stream)."""
     n = eng.n
     main = torch.cuda.current_stream()
     if isinstance(image_arrays, torch.Tensor):   # [N,h,w,3] uint8 (e.g. pinned host memory)
@@ -229,17 +229,13 @@ class ServingDriver(object):
         batch = slot['raw_host']
       if slot['raw_dev'] is None or tuple(slot['raw_dev'].shape) != shape:
         slot['raw_dev'] = torch.empty(shape, dtype=torch.uint8, device=self.device)
-      # upload AND pre-process on the copy stream: the engine input is free as soon as the stem of
-      # the previous request has run (Engine.input_free), so the 80 us pre-process kernel of this
-      # request overlaps the rest of that request's backbone instead of preceding this one's
       with torch.cuda.stream(self._copy_stream):
         self._copy_stream.wait_event(slot['ev_raw_free'])   # pre-process of the request before last
         slot['raw_dev'].copy_(batch, non_blocking=True)
-        self._copy_stream.wait_event(eng.input_free)
-        scale = ops.preprocess(slot['raw_dev'], eng.input, self.mean_rgb, self.stddev_rgb)
-        slot['ev_raw_free'].record(self._copy_stream)
         slot['ev_h2d'].record(self._copy_stream)
       main.wait_event(slot['ev_h2d'])
+      scale = ops.preprocess(slot['raw_dev'], eng.input, self.mean_rgb, self.stddev_rgb)
+      slot['ev_raw_free'].record(main)
       slot['scales'].fill_(scale)
     else:  # ragged batch: one pre-process launch per image (like the reference's python loop)
       for i, im in enumerate(image_arrays):
