@@ -82,6 +82,46 @@ def device_weights(arch, w, round_gemm_weights=True):
   return out
 
 
+def effnetv2_device_weights(arch, w):
+  """The same for the EfficientNet V1 / V2 backbone (efficientnetv2/effnetv2_model.py::_build): BN
+  folded into fp16 conv kernels (1x1 and k x k), fp32 depthwise taps."""
+  out = dict(w)
+  mn, eps = arch.model_name, arch.bn_eps
+
+  def fold(kernel, bn, depthwise=False):
+    g, b = np.float64(w[bn + '/gamma']), np.float64(w[bn + '/beta'])
+    m, v = np.float64(w[bn + '/moving_mean']), np.float64(w[bn + '/moving_variance'])
+    s = g / np.sqrt(v + eps)
+    k = np.float64(w[kernel]) * (s.reshape(1, 1, -1, 1) if depthwise else s.reshape(1, 1, 1, -1))
+    out[kernel] = k.astype(np.float32) if depthwise else _r16(k)
+    out[bn + '/gamma'] = np.ones_like(g, np.float32)
+    out[bn + '/moving_variance'] = np.full(g.shape, 1.0 - eps, np.float32)
+    out[bn + '/moving_mean'] = np.zeros_like(g, np.float32)
+    out[bn + '/beta'] = (b - m * s).astype(np.float32)
+
+  fold(mn + '/stem/conv2d/kernel', mn + '/stem/batch_normalization')
+  for b in arch.blocks:
+    sc = '%s/%s' % (mn, b.name)
+    convs = iter(['conv2d', 'conv2d_1'])
+    bns = iter(['tpu_batch_normalization', 'tpu_batch_normalization_1', 'tpu_batch_normalization_2'])
+    if b.expand_ratio != 1:
+      fold('%s/%s/kernel' % (sc, next(convs)), '%s/%s' % (sc, next(bns)))
+    if b.conv_type == 0:
+      fold(sc + '/depthwise_conv2d/depthwise_kernel', '%s/%s' % (sc, next(bns)), depthwise=True)
+    fold('%s/%s/kernel' % (sc, next(convs)), '%s/%s' % (sc, next(bns)))
+  fold(mn + '/head/conv2d/kernel', mn + '/head/batch_normalization')
+  return out
+
+
+def effnetv2_format_errors(arch, w, x):
+  """{endpoint: rel-L2 of the format model vs the fp32 oracle} and the fp32 endpoints."""
+  from oracle import effnetv2_oracle  # pylint: disable=g-import-not-at-top
+  ref = effnetv2_oracle.EffNetV2Oracle(arch, w, torch.float32)(x)
+  mod = effnetv2_oracle.EffNetV2Oracle(arch, effnetv2_device_weights(arch, w), torch.float32,
+                                       store=eo.fp16_store)(x)
+  return {k: DeviceModel.rel_l2(mod[k], ref[k]) for k in ref}, ref
+
+
 class DeviceModel(object):
   """fp32 oracle + the oracle at device precision for one (config, weights, input)."""
 

@@ -149,9 +149,9 @@ def test_d7x_1536():
 
 
 def test_effnetv2_s_384():
-  """BASELINE config 3 at its own resolution (batch 2 of the 128)."""
+  """BASELINE config 3 at its own resolution (batch 2 of the 128): every endpoint within 2e-3
+  absolute and within 1.5x the format model (tests/precision_model.py) + 1e-4."""
   from automl_b200.efficientnetv2 import effnetv2_model
-  from oracle import effnetv2_oracle
   name = 'efficientnetv2-s'
   a = effnetv2_model.EffNetV2Arch(name)
   w = effnetv2_model.synthetic_weights(a, 11)
@@ -159,11 +159,15 @@ def test_effnetv2_s_384():
   x = np.random.default_rng(3).uniform(-1, 1, size=(2, 384, 384, 3)).astype(np.float32)
   model(torch.from_numpy(x), with_endpoints=True)
   torch.cuda.synchronize()
-  ref = effnetv2_oracle.EffNetV2Oracle(a, w, torch.float32)(x)
+  import precision_model as pm
+  merr, ref = pm.effnetv2_format_errors(a, w, x)     # what fp16 storage alone costs (no kernel)
   errs = {k: rel_l2(t.float().cpu().permute(0, 3, 1, 2), ref[k]) for k, t in model.endpoints.items()}
   _record('efficientnetv2-s 384x384 batch 2', {'worst': max(errs.values()),
-                                              'stem_to_stage2': max(errs[k] for k in errs if k in ('stem', 'reduction_1', 'reduction_2'))})
+                                              'stem_to_stage2': max(errs[k] for k in errs if k in ('stem', 'reduction_1', 'reduction_2')),
+                                              'format_model_worst': max(merr.values())})
   assert max(errs.values()) < 2e-3, errs
+  for k, e in errs.items():       # the last stage is past 1e-3 because the FORMAT is (1.59e-3 in the model)
+    assert e < pm.bar(merr[k]), (k, e, merr[k])
 
 
 @pytest.mark.parametrize('method', ['gaussian', 'hard'])

@@ -45,3 +45,20 @@ def test_format_model_explains_the_ill_conditioned_sum_draw():
     m = pm.DeviceModel(c, a, w, x)
     errs[seed] = max(m.box_error(l) for l in a.levels)
   assert errs[0] < 8e-4 < 1e-3 < errs[3]
+
+
+def test_effnetv2_fold_is_exact_and_model_is_small_on_b0():
+  from automl_b200.efficientnetv2 import effnetv2_model
+  from oracle import effnetv2_oracle
+  a = effnetv2_model.EffNetV2Arch('efficientnetv2-b0')
+  w = effnetv2_model.synthetic_weights(a, 11)
+  x = np.random.default_rng(3).uniform(-1, 1, size=(1, 64, 64, 3)).astype(np.float32)
+  errs, ref = pm.effnetv2_format_errors(a, w, x)
+  assert set(errs) == set(ref) and 1e-4 < max(errs.values()) < 1.5e-3
+  # in float64 the fold is exact, so rounding the folded GEMM weights to fp16 is the only difference
+  # left between the two networks: small but non-zero
+  folded = pm.effnetv2_device_weights(a, w)
+  ref64 = effnetv2_oracle.EffNetV2Oracle(a, w, torch.float64)(x)
+  mod64 = effnetv2_oracle.EffNetV2Oracle(a, folded, torch.float64)(x)
+  e = pm.DeviceModel.rel_l2(mod64['head_1x1'], ref64['head_1x1'])
+  assert 1e-5 < e < 1e-3
